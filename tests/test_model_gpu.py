@@ -1,0 +1,173 @@
+"""GPU parity of the model path (mel -> encode_audio -> transcribe_streaming, generate_step) on a
+tiny synthetic GGUF, against the CPU oracle, through the C ABI.
+
+Tolerances (f32 path; the north_star bounds encoder hidden states at 1e-3 abs):
+  mel log-spectrogram 2e-4 abs; audio embeds 1e-3 abs (asserted much tighter here, tiny model);
+  logits 1e-3 abs; token ids bit-exact (the oracle's top-2 margin is asserted to dominate the error).
+"""
+import numpy as np
+import pytest
+
+from oracle import mel as omel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tiny_model(vx, tiny_gguf):
+    m = vx.Q4ModelLoader.from_file(tiny_gguf).load(0, max_batch=4, max_mel_frames=3000)
+    yield m
+    m.close()
+
+
+def _mel(seconds, seed=1234):
+    a = omel.peak_normalize(omel.speechlike(seconds, seed))
+    return a, omel.mel_tensor_from_audio(a)
+
+
+def test_mel_gpu_vs_oracle(vx):
+    ms = vx.MelSpectrogram.voxtral(0)
+    o = omel.MelSpectrogram()
+    assert np.abs(ms.window() - o.window).max() < 1e-7
+    fb, ofb = ms.mel_basis(), o.mel_basis
+    assert np.abs(fb - ofb).max() < 1e-6 * ofb.max() + 1e-9
+    for sig in (omel.sine_16k(1.0), omel.noise_chirp(3.0), omel.pad_audio(omel.speechlike(2.0)),
+                np.zeros(16000, np.float32), omel.speechlike(0.3)[:3333]):
+        g = ms.compute_log(sig)
+        e = o.compute_log(sig)
+        assert g.shape == e.shape == (omel.num_frames(sig.size), 128)
+        assert np.abs(g - e).max() < 2e-4, np.abs(g - e).max()
+    # reference pins (mel.rs:409-421, 438-456): silence -> floor, 440 Hz sine in [-2, 3]
+    assert np.all(ms.compute_log(np.zeros(16000, np.float32)) == np.float32((-6.5 + 4.0) / 4.0))
+    s = ms.compute_log(omel.sine_16k(1.0))
+    assert s.min() >= -2.0 and s.max() <= 3.0
+
+
+def test_encode_audio_parity(tiny_model, tiny_oracle):
+    _, mel = _mel(4.0)
+    got = tiny_model.encode_audio(mel)
+    cap = {}
+    exp = tiny_oracle.encode_audio(mel, capture=cap).numpy()
+    assert got.shape == (1,) + exp.shape
+    err = np.abs(got[0] - exp).max()
+    assert err < 1e-3
+    assert err < 5e-5 * max(1.0, np.abs(exp).max()), err
+    enc = tiny_model.debug("enc_out").reshape(cap["enc_out"].shape)
+    assert np.abs(enc - cap["enc_out"].numpy()).max() < 1e-3
+
+
+def test_encoder_layers_capture(tiny_model, tiny_oracle):
+    _, mel = _mel(2.0, seed=9)
+    tiny_model.debug("capture_on")
+    tiny_model.encode_audio(mel)
+    cap = {}
+    tiny_oracle.encode_audio(mel, capture=cap)
+    conv = tiny_model.debug("conv").reshape(cap["conv"].shape)
+    assert np.abs(conv - cap["conv"].numpy()).max() < 1e-4
+    for i in range(tiny_oracle.cfg.enc_layers):
+        g = tiny_model.debug(f"enc{i}").reshape(cap[f"enc{i}"].shape)
+        assert np.abs(g - cap[f"enc{i}"].numpy()).max() < 2e-4, i
+    tiny_model.debug("capture_off")
+
+
+def test_sliding_window_bites(tiny_model, tiny_oracle):
+    """tiny enc_window=20 < S: the window mask changes the result, and we match the oracle."""
+    _, mel = _mel(3.0, seed=4)
+    got = tiny_model.encode_audio(mel)[0]
+    exp = tiny_oracle.encode_audio(mel).numpy()
+    assert np.abs(got - exp).max() < 1e-3
+    saved = tiny_oracle.cfg.enc_window
+    tiny_oracle.cfg.enc_window = 100000
+    try:
+        nowin = tiny_oracle.encode_audio(mel).numpy()
+    finally:
+        tiny_oracle.cfg.enc_window = saved
+    assert np.abs(nowin - exp).max() > 10 * np.abs(got - exp).max()
+
+
+def test_transcribe_streaming_token_parity(vx, tiny_model, tiny_oracle):
+    _, mel = _mel(4.0)
+    t_embed = omel.time_embedding(6.0, tiny_oracle.cfg.dec_dim)
+    info = {}
+    exp = tiny_oracle.transcribe_streaming(mel, t_embed, info=info)
+    tm = vx.Timings()
+    got = tiny_model.transcribe_streaming(mel, timings=tm)
+    assert len(exp) == mel.shape[2] // 16 - 38 == tm.decode_tokens
+    assert got == exp, (got, exp, min(info["margins"]))
+    assert len(set(exp)) > 2          # not a degenerate constant sequence
+    assert tm.decode_ms > 0 and tm.encode_ms > 0
+    # eager (no CUDA graph) path gives the same ids
+    tiny_model.debug("graph_off")
+    assert tiny_model.transcribe_streaming(mel) == exp
+    tiny_model.debug("graph_on")
+
+
+def test_transcribe_short_audio_returns_empty(tiny_model):
+    mel = np.zeros((1, 128, 37 * 16), np.float32)  # seq_len 37 < 38 (model.rs:887-889)
+    assert tiny_model.transcribe_streaming(mel) == []
+
+
+def test_transcribe_pcm_pipeline_and_batch(vx, tiny_model, tiny_oracle):
+    """PCM entry point (device peak-normalise + pad + GPU mel) == oracle pipeline; batched streams
+    give exactly the per-stream results."""
+    sigs = [omel.speechlike(3.0, seed=s) for s in (11, 12, 13)]
+    t_embed = omel.time_embedding(6.0, tiny_oracle.cfg.dec_dim)
+    exp = []
+    for s in sigs:
+        mel = omel.mel_tensor_from_audio(omel.peak_normalize(s))
+        exp.append(tiny_oracle.transcribe_streaming(mel, t_embed))
+    got_b = tiny_model.transcribe_pcm(np.stack(sigs))
+    assert got_b.shape == (3, len(exp[0]))
+    for i in range(3):
+        assert got_b[i].tolist() == exp[i], i
+        assert tiny_model.transcribe_pcm(sigs[i])[0].tolist() == exp[i]
+
+
+def test_generate_step_with_cache_parity(tiny_model, tiny_oracle):
+    """Incremental API (model.rs:857-867): prefill M=5 then single steps; logits vs oracle."""
+    cfg = tiny_oracle.cfg
+    t_embed = omel.time_embedding(6.0, cfg.dec_dim)
+    ada = tiny_oracle.ada_scales(t_embed)
+    cache = tiny_oracle.new_cache()
+    tiny_model.reset_cache()
+    ids = [1, 32, 77, 400, 9]
+    h = tiny_oracle.decoder_forward_with_cache(tiny_oracle.embed_tokens(ids), ada, cache)
+    exp = tiny_oracle.lm_head(h).numpy()
+    got = tiny_model.generate_step_with_cache(np.array([ids]))
+    assert got.shape == (1, 5, cfg.vocab)
+    assert np.abs(got[0] - exp).max() < 1e-3
+    assert tiny_model.cache_len() == 5
+    for tok in (123, 7):
+        h = tiny_oracle.decoder_forward_with_cache(tiny_oracle.embed_tokens([tok]), ada, cache)
+        exp = tiny_oracle.lm_head(h).numpy()
+        got = tiny_model.generate_step_with_cache(np.array([[tok]]))
+        assert np.abs(got[0] - exp).max() < 1e-3
+        assert int(got[0, 0].argmax()) == int(exp[0].argmax())
+    assert tiny_model.cache_len() == 7
+    # different fed-back token => different logits (feedback path is live)
+    a = tiny_model.generate_step_with_cache(np.array([[5]]))
+    tiny_model.reset_cache()
+    assert tiny_model.cache_len() == 0
+    b = tiny_model.generate_step_with_cache(np.array([[6]]))
+    assert np.abs(a - b).max() > 1e-3
+
+
+def test_set_delay_changes_ada(tiny_model, tiny_oracle):
+    cfg = tiny_oracle.cfg
+    for delay in (6.0, 2.0):
+        tiny_model.set_delay(delay)
+        ada = np.stack([a.numpy() for a in tiny_oracle.ada_scales(omel.time_embedding(delay, cfg.dec_dim))])
+        got = tiny_model.debug("ada").reshape(ada.shape)
+        assert np.abs(got - ada).max() < 1e-5
+    tiny_model.set_delay(6.0)
+
+
+def test_loader_errors(vx, tiny_gguf, tmp_path):
+    with pytest.raises(vx.VoxtralError, match="Failed to open"):
+        vx.Q4ModelLoader.from_file(str(tmp_path / "missing.gguf"))
+    # a GGUF lacking a required tensor -> "Tensor '...' not found"
+    from oracle import gguf_synth, q4 as oq4
+    raw = oq4.quantize_f32_to_q4_0(np.ones(32 * 32, np.float32))
+    data = gguf_synth.build_gguf_bytes([("weight_a", 2, (32, 32), raw)])
+    with pytest.raises(vx.VoxtralError, match="not found"):
+        vx.Q4ModelLoader.from_bytes(data).load(0)

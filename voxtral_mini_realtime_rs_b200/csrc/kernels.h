@@ -1,0 +1,90 @@
+// kernels.h -- host-callable launchers for the sm_100a kernels (all asynchronous on `st`).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace vox {
+
+// Repacked Q4_0 weight resident in HBM.  The 18-byte GGUF blocks {f16 d; u8 qs[16]} are split at
+// load into a 16-byte-aligned nibble plane and an f16 scale plane (row-major by n, K-blocks
+// contiguous) so that a warp reads 512 contiguous bytes per request.  Dequant rule unchanged:
+// element i of a block = (qs[i] & 15) - 8, element i+16 = (qs[i] >> 4) - 8, times d.
+struct Q4Weight {
+    const uint4 *qs = nullptr;   // [N][K/32]
+    const __half *d = nullptr;   // [N][K/32]
+    int N = 0, K = 0;
+    size_t bytes() const { return (size_t)N * (K / 32) * 18; }
+};
+
+enum Epi : int {
+    EPI_NONE = 0,      // y = acc (+bias)
+    EPI_RESIDUAL = 1,  // y = res + acc (+bias)     (y may alias res)
+    EPI_SILU_MUL = 2,  // rows (2i,2i+1) = (gate_i, up_i): y[:, i] = silu(gate) * up, ldy = N/2
+    EPI_GELU = 3,      // y = gelu_erf(acc + bias)
+};
+
+// y[M,N] = x[M,K] . W^T, M <= 8 (decode / batched decode): warp-per-row-pair, shuffle reduce.
+void launch_q4_matvec(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias,
+                      const float *res, int epi, cudaStream_t st);
+// y[M,N] = A[M,K] . W^T for any M (encoder / prefill): tiled SIMT GEMM, in-tile dequant.
+void launch_q4_gemm(const Q4Weight &w, const float *a, int M, float *y, int ldy, const float *bias,
+                    const float *res, int epi, cudaStream_t st);
+// conv2 as implicit GEMM: in [B][T_in][C_in] time-major, W [C_out][3*C_in] (k = tap*C_in + c),
+// stride 2, pad 1, + bias, GELU -> out [B][T_out][C_out].
+void launch_conv2_gemm(const float *in, const float *w, const float *bias, float *out, int B, int T_in,
+                       int T_out, int C_in, int C_out, cudaStream_t st);
+// conv1: mel [B][C_in][T] channel-major, W [C_out][C_in][3] -> GELU -> out [B][T_out][C_out].
+void launch_conv1(const float *mel, const float *w, const float *bias, float *out, int B, int C_in, int T,
+                  int T_out, int C_out, cudaStream_t st);
+
+// y = x / sqrt(mean(x^2)+eps) * gamma (* scale, optional ADA vector)
+void launch_rmsnorm(const float *x, const float *gamma, const float *scale, float *y, int rows, int dim,
+                    float eps, cudaStream_t st);
+// in-place interleaved-pair RoPE on q (n_q heads) and k (n_k heads) inside a fused row buffer;
+// row r has position pos0 + (r % seq).  cos/sin: [max_pos][hd/2].
+void launch_rope_inplace(float *buf, int rows, int ld, int q_off, int n_q, int k_off, int n_k, int hd,
+                         int seq, int pos0, const float *cos_t, const float *sin_t, cudaStream_t st);
+// encoder attention: causal + sliding window (|i-j| <= window), per (batch, head); qkv rows
+// [B*S][ld] with q at q_off, k at k_off, v at v_off; out [B*S][H*hd].
+void launch_enc_attention(const float *qkv, float *out, int B, int S, int H, int hd, int ld, int q_off,
+                          int k_off, int v_off, int window, float scale, cudaStream_t st);
+// decoder: RoPE q in place, RoPE k -> Kcache, v -> Vcache at positions *pos_ptr + i.
+// qkv rows [B*M][ld]; caches [B][Hkv][max_seq][hd].
+void launch_dec_rope_append(float *qkv, int B, int M, int ld, int H, int Hkv, int hd, float *kc, float *vc,
+                            int max_seq, const int *pos_ptr, const float *cos_t, const float *sin_t,
+                            cudaStream_t st);
+// decoder GQA attention over the cache (keys 0..*pos_ptr+i, window), out [B*M][H*hd].
+void launch_dec_attention(const float *qkv, int B, int M, int ld, int H, int Hkv, int hd, const float *kc,
+                          const float *vc, int max_seq, const int *pos_ptr, int window, float scale,
+                          float *out, cudaStream_t st);
+// x[r][:] = (audio ? audio[b][*pos_ptr + i][:] : 0) + dequant(E[ids[r]]),  r = b*M + i
+void launch_embed(const Q4Weight &emb, const int *ids, const float *audio, int audio_seq, int B, int M,
+                  const int *pos_ptr, float *x, cudaStream_t st);
+// greedy argmax (lowest index wins ties) over logits [B][V]; writes tok[b] and, if out_ids,
+// out_ids[b*out_ld + *out_pos_ptr]
+void launch_argmax(const float *logits, int B, int V, int *tok, int *out_ids, int out_ld,
+                   const int *out_pos_ptr, cudaStream_t st);
+// *a += da; *b += db  (device-side step counters for graph replay)
+void launch_advance(int *a, int da, int *b, int db, cudaStream_t st);
+// gather rows: dst[b][:] = src[b*M + (M-1)][:]
+void launch_gather_last(const float *src, float *dst, int B, int M, int dim, cudaStream_t st);
+// reshape_encoder_output is a pure view when S % factor == 0; otherwise rows are re-packed
+void launch_reshape_rows(const float *src, float *dst, int B, int S, int S_out, int dim, int factor,
+                         cudaStream_t st);
+// GELU in place
+void launch_gelu(float *x, size_t n, cudaStream_t st);
+
+// mel: samples [B][n] device -> log-mel; layout 0 [B][frames][128], 1 [B][128][frames]
+void launch_mel(const float *samples, int B, size_t n, size_t sample_stride, const float *window,
+                const float *fb_vals, const int *fb_start, const int *fb_len, int fb_stride, float *out,
+                int frames, int layout, cudaStream_t st);
+// peak normalisation on device: per stream max|x| then scale (target/max), skip if max < 1e-10;
+// writes into a padded buffer at offset left (rest pre-zeroed by caller)
+void launch_peak_normalize_pad(const float *in, int B, size_t n, float target, int do_norm, float *out,
+                               size_t out_stride, size_t left, float *scale_buf, cudaStream_t st);
+
+uint64_t kernel_launch_count();
+
+}  // namespace vox

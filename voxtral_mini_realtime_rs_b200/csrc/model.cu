@@ -1,0 +1,586 @@
+// model.cu -- GGUF -> HBM loader (with load-time Q4 repack) and the session that runs
+// encode_audio / prefill / decode on one CUDA stream.  Graph semantics follow the reference's
+// src/gguf/model.rs (cited per function); nothing here is a translation of its Burn code.
+#include "model.h"
+
+#include <cmath>
+#include <cstring>
+
+#include "common.h"
+
+namespace vox {
+
+void cuda_check(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) fail(VOX_ECUDA, fmt("CUDA error: %s: %s", what, cudaGetErrorString(e)));
+}
+
+void *DeviceArena::alloc(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) fail(VOX_ENOMEM, fmt("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)));
+    ptrs.push_back(p);
+    total += bytes;
+    return p;
+}
+
+void DeviceArena::release() {
+    for (void *p : ptrs) cudaFree(p);
+    ptrs.clear();
+    total = 0;
+}
+
+void MelTables::build(DeviceArena &arena) {
+    fb_dense.resize((size_t)kMelBins * kMelFreqs);
+    mel_filterbank(fb_dense.data());
+    window_host.resize(kMelNfft);
+    hann_window(kMelNfft, window_host.data());
+    // sparse spans: [start, start+len) covers every non-zero of the dense row, in ascending bin
+    // order so the sum equals the reference's dense sequential sum (adding 0.0 is exact).
+    std::vector<int> start(kMelBins), len(kMelBins);
+    int maxlen = 1;
+    for (int m = 0; m < kMelBins; ++m) {
+        int lo = kMelFreqs, hi = -1;
+        for (int j = 0; j < kMelFreqs; ++j)
+            if (fb_dense[(size_t)m * kMelFreqs + j] != 0.0f) { lo = std::min(lo, j); hi = std::max(hi, j); }
+        if (hi < 0) { lo = 0; hi = -1; }
+        start[m] = lo;
+        len[m] = hi - lo + 1;
+        maxlen = std::max(maxlen, len[m]);
+    }
+    fb_stride = maxlen;
+    std::vector<float> vals((size_t)kMelBins * maxlen, 0.0f);
+    for (int m = 0; m < kMelBins; ++m)
+        for (int j = 0; j < len[m]; ++j) vals[(size_t)m * maxlen + j] = fb_dense[(size_t)m * kMelFreqs + start[m] + j];
+    window = arena.upload(window_host.data(), window_host.size());
+    fb_vals = arena.upload(vals.data(), vals.size());
+    fb_start = arena.upload(start.data(), start.size());
+    fb_len = arena.upload(len.data(), len.size());
+}
+
+Q4Weight upload_q4(DeviceArena &arena, const std::vector<const uint8_t *> &raw, const std::vector<int> &n_rows,
+                   int K, bool interleave) {
+    VOX_CHECK(K % 32 == 0, VOX_EINVAL, "Q4 weight with K=%d (not a multiple of 32)", K);
+    const int bpr = K / 32;
+    int N = 0;
+    for (int n : n_rows) N += n;
+    if (interleave) VOX_CHECK(raw.size() == 2 && n_rows[0] == n_rows[1], VOX_EINVAL, "interleave needs two equal parts");
+    std::vector<uint8_t> qs((size_t)N * bpr * 16);
+    std::vector<uint16_t> ds((size_t)N * bpr);
+    int row_base = 0;
+    for (size_t p = 0; p < raw.size(); ++p) {
+        for (int r = 0; r < n_rows[p]; ++r) {
+            const int dst_row = interleave ? 2 * r + (int)p : row_base + r;
+            const uint8_t *src = raw[p] + (size_t)r * bpr * 18;
+            uint8_t *qd = qs.data() + (size_t)dst_row * bpr * 16;
+            uint16_t *dd = ds.data() + (size_t)dst_row * bpr;
+            for (int b = 0; b < bpr; ++b) {
+                memcpy(dd + b, src + (size_t)b * 18, 2);
+                memcpy(qd + (size_t)b * 16, src + (size_t)b * 18 + 2, 16);
+            }
+        }
+        row_base += n_rows[p];
+    }
+    Q4Weight w;
+    w.N = N;
+    w.K = K;
+    w.qs = (const uint4 *)arena.upload(qs.data(), qs.size());
+    w.d = (const __half *)arena.upload(ds.data(), ds.size());
+    return w;
+}
+
+namespace {
+
+const char *kEnc = "mm_streams_embeddings.embedding_module.whisper_encoder";
+const char *kAdapter = "mm_streams_embeddings.embedding_module.audio_language_projection";
+const char *kTokEmb = "mm_streams_embeddings.embedding_module.tok_embeddings.weight";
+const char *kFinalNorm = "norm.weight";
+
+float f16_to_f32(uint16_t h) {
+    uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu, bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {
+            int e = -1;
+            do { e++; man <<= 1; } while ((man & 0x400u) == 0);
+            man &= 0x3FFu;
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | (man << 13);
+        }
+    } else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+    else bits = sign | ((exp + 127 - 15) << 23) | (man << 13);
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
+struct Loader {
+    const Gguf &g;
+    Model &m;
+    uint64_t q4_bytes = 0;
+
+    const GgufTensorInfo &info(const std::string &name) {
+        const GgufTensorInfo *t = g.find(name);
+        VOX_CHECK(t != nullptr, VOX_ENOTFOUND, "Tensor '%s' not found in GGUF", name.c_str());
+        return *t;
+    }
+    bool has(const std::string &name) { return g.find(name) != nullptr; }
+
+    // load_f32_tensor (loader.rs:443-474): F32/F16 -> f32; shape checked.
+    std::vector<float> f32(const std::string &name, const std::vector<int64_t> &shape) {
+        const GgufTensorInfo &t = info(name);
+        VOX_CHECK(t.dtype != VOX_DTYPE_Q4_0, VOX_EFORMAT, "Cannot load Q4_0 tensor '%s' as f32", name.c_str());
+        VOX_CHECK(t.shape() == shape, VOX_EINVAL, "Tensor '%s' has unexpected shape", name.c_str());
+        std::vector<uint8_t> raw((size_t)t.byte_size());
+        g.read_tensor(t, raw.data());
+        size_t n = (size_t)t.num_elements();
+        std::vector<float> out(n);
+        if (t.dtype == VOX_DTYPE_F32) memcpy(out.data(), raw.data(), n * 4);
+        else
+            for (size_t i = 0; i < n; ++i) {
+                uint16_t h;
+                memcpy(&h, raw.data() + 2 * i, 2);
+                out[i] = f16_to_f32(h);
+            }
+        return out;
+    }
+    float *f32_dev(const std::string &name, const std::vector<int64_t> &shape) {
+        std::vector<float> v = f32(name, shape);
+        return m.arena.upload(v.data(), v.size());
+    }
+    // load_q4_linear (loader.rs:390-405): dtype must be Q4_0; shape [N,K] checked.
+    std::vector<uint8_t> q4_raw(const std::string &name, int N, int K) {
+        const GgufTensorInfo &t = info(name);
+        VOX_CHECK(t.dtype == VOX_DTYPE_Q4_0, VOX_EFORMAT, "Expected Q4_0 for '%s', got dtype %u", name.c_str(), t.dtype);
+        std::vector<int64_t> shp = t.shape();
+        VOX_CHECK(shp.size() == 2 && shp[0] == N && shp[1] == K, VOX_EINVAL, "Tensor '%s' has unexpected shape (want [%d,%d])",
+                  name.c_str(), N, K);
+        std::vector<uint8_t> raw((size_t)t.byte_size());
+        g.read_tensor(t, raw.data());
+        q4_bytes += raw.size();
+        return raw;
+    }
+    Q4Weight q4(const std::string &name, int N, int K) {
+        std::vector<uint8_t> raw = q4_raw(name, N, K);
+        return upload_q4(m.arena, {raw.data()}, {N}, K, false);
+    }
+    Q4Weight q4_concat(const std::vector<std::string> &names, const std::vector<int> &ns, int K) {
+        std::vector<std::vector<uint8_t>> raws;
+        std::vector<const uint8_t *> ptrs;
+        for (size_t i = 0; i < names.size(); ++i) raws.push_back(q4_raw(names[i], ns[i], K));
+        for (auto &r : raws) ptrs.push_back(r.data());
+        return upload_q4(m.arena, ptrs, ns, K, false);
+    }
+    Q4Weight q4_interleave(const std::string &a, const std::string &b, int N, int K) {
+        std::vector<uint8_t> ra = q4_raw(a, N, K), rb = q4_raw(b, N, K);
+        return upload_q4(m.arena, {ra.data(), rb.data()}, {N, N}, K, true);
+    }
+    // optional bias (loader.rs:428-437): zeros when the tensor is absent
+    std::vector<float> bias_or_zero(const std::string &name, int n) {
+        if (has(name)) return f32(name, {n});
+        return std::vector<float>((size_t)n, 0.0f);
+    }
+};
+
+void build_rope(DeviceArena &arena, int hd, int max_seq, float theta, float **cos_d, float **sin_d) {
+    // RoPEConfig::init (rope.rs:35-64), f32 throughout
+    const int half = hd / 2;
+    std::vector<float> inv(half), c((size_t)max_seq * half), s((size_t)max_seq * half);
+    for (int i = 0; i < half; ++i) inv[i] = 1.0f / powf(theta, (float)(2 * i) / (float)hd);
+    for (int p = 0; p < max_seq; ++p)
+        for (int i = 0; i < half; ++i) {
+            const float f = (float)p * inv[i];
+            c[(size_t)p * half + i] = cosf(f);
+            s[(size_t)p * half + i] = sinf(f);
+        }
+    *cos_d = arena.upload(c.data(), c.size());
+    *sin_d = arena.upload(s.data(), s.size());
+}
+
+}  // namespace
+
+Model *Model::load(const Gguf &g, int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    VOX_CHECK(e == cudaSuccess && ndev > 0, VOX_ECUDA, "no CUDA device available (%s); this library has no CPU fallback",
+              cudaGetErrorString(e));
+    VOX_CHECK(device >= 0 && device < ndev, VOX_EINVAL, "device %d out of range (have %d)", device, ndev);
+    CUDA_OK(cudaSetDevice(device));
+    Model *mp = new Model();
+    try {
+        Model &m = *mp;
+        m.device = device;
+        m.arena.device = device;
+        Loader L{g, m};
+        vox_model_info &c = m.info;
+        // ---- dims: optional voxtral.* KVs, else the reference defaults (config.rs:441-486) ----
+        auto kv = [&](const char *k, int dflt) { uint32_t v; return g.kv_u32(k, &v) ? (int)v : dflt; };
+        c.enc_layers = kv("voxtral.enc.n_layers", 32);
+        c.enc_heads = kv("voxtral.enc.n_heads", 32);
+        c.enc_head_dim = kv("voxtral.enc.head_dim", 64);
+        c.enc_window = kv("voxtral.enc.sliding_window", 750);
+        c.dec_layers = kv("voxtral.dec.n_layers", 26);
+        c.dec_heads = kv("voxtral.dec.n_heads", 32);
+        c.dec_kv_heads = kv("voxtral.dec.n_kv_heads", 8);
+        c.dec_head_dim = kv("voxtral.dec.head_dim", 128);
+        c.dec_window = kv("voxtral.dec.sliding_window", 8192);
+        c.reshape_factor = kv("voxtral.reshape_factor", 4);
+        c.prefix_len = 38;
+        const std::string E = kEnc;
+        {
+            std::vector<int64_t> s = L.info(E + ".conv_layers.0.conv.weight").shape();
+            VOX_CHECK(s.size() == 3 && s[2] == 3, VOX_EINVAL, "conv_layers.0 weight must be [C,mels,3]");
+            c.enc_dim = (int)s[0];
+            c.n_mels = (int)s[1];
+            VOX_CHECK(c.n_mels == kMelBins, VOX_EINVAL, "n_mels=%d unsupported (mel front-end is 128-bin)", c.n_mels);
+        }
+        c.enc_ffn = (int)L.info(E + ".transformer.layers.0.feed_forward.w1.weight").shape()[0];
+        {
+            std::vector<int64_t> s = L.info(kTokEmb).shape();
+            c.vocab = (int)s[0];
+            c.dec_dim = (int)s[1];
+        }
+        c.dec_ffn = (int)L.info("layers.0.feed_forward.w1.weight").shape()[0];
+        c.t_cond_dim = (int)L.info("layers.0.ada_rms_norm_t_cond.0.weight").shape()[0];
+        VOX_CHECK(c.dec_heads % c.dec_kv_heads == 0, VOX_EINVAL, "dec_heads %% dec_kv_heads != 0");
+        VOX_CHECK(c.enc_head_dim == 32 || c.enc_head_dim == 64 || c.enc_head_dim == 128, VOX_EINVAL,
+                  "encoder head_dim %d unsupported", c.enc_head_dim);
+        VOX_CHECK(c.dec_head_dim % 4 == 0, VOX_EINVAL, "decoder head_dim %d unsupported", c.dec_head_dim);
+
+        const int d = c.enc_dim, hdq = c.enc_heads * c.enc_head_dim, D = c.dec_dim;
+        // ---- conv downsampler (loader.rs:263-275), f32 ----
+        m.conv1_w = L.f32_dev(E + ".conv_layers.0.conv.weight", {d, c.n_mels, 3});
+        m.conv1_b = L.f32_dev(E + ".conv_layers.0.conv.bias", {d});
+        {
+            std::vector<float> w = L.f32(E + ".conv_layers.1.conv.weight", {d, d, 3});
+            std::vector<float> r((size_t)d * 3 * d);  // [o][tap*C + c] for the implicit GEMM
+            for (int o = 0; o < d; ++o)
+                for (int ci = 0; ci < d; ++ci)
+                    for (int t = 0; t < 3; ++t) r[(size_t)o * 3 * d + (size_t)t * d + ci] = w[((size_t)o * d + ci) * 3 + t];
+            m.conv2_w = m.arena.upload(r.data(), r.size());
+        }
+        m.conv2_b = L.f32_dev(E + ".conv_layers.1.conv.bias", {d});
+        // ---- encoder layers (loader.rs:215-260) ----
+        m.enc.resize(c.enc_layers);
+        for (int i = 0; i < c.enc_layers; ++i) {
+            const std::string p = E + ".transformer.layers." + std::to_string(i);
+            EncLayerW &l = m.enc[i];
+            l.attn_norm = L.f32_dev(p + ".attention_norm.weight", {d});
+            l.ffn_norm = L.f32_dev(p + ".ffn_norm.weight", {d});
+            l.wqkv = L.q4_concat({p + ".attention.wq.weight", p + ".attention.wk.weight", p + ".attention.wv.weight"},
+                                 {hdq, hdq, hdq}, d);
+            std::vector<float> bq = L.bias_or_zero(p + ".attention.wq.bias", hdq);
+            std::vector<float> bv = L.bias_or_zero(p + ".attention.wv.bias", hdq);
+            std::vector<float> bqkv((size_t)3 * hdq, 0.0f);  // wk has no bias (loader.rs:229)
+            memcpy(bqkv.data(), bq.data(), sizeof(float) * hdq);
+            memcpy(bqkv.data() + 2 * hdq, bv.data(), sizeof(float) * hdq);
+            l.bqkv = m.arena.upload(bqkv.data(), bqkv.size());
+            l.wo = L.q4(p + ".attention.wo.weight", d, hdq);
+            std::vector<float> bo = L.bias_or_zero(p + ".attention.wo.bias", d);
+            l.bo = m.arena.upload(bo.data(), bo.size());
+            l.w13 = L.q4_interleave(p + ".feed_forward.w1.weight", p + ".feed_forward.w3.weight", c.enc_ffn, d);
+            l.w2 = L.q4(p + ".feed_forward.w2.weight", d, c.enc_ffn);
+            std::vector<float> b2 = L.bias_or_zero(p + ".feed_forward.w2.bias", d);
+            l.b2 = m.arena.upload(b2.data(), b2.size());
+        }
+        m.enc_norm = L.f32_dev(E + ".transformer.norm.weight", {d});
+        // ---- adapter (loader.rs:377-383) ----
+        m.adapter0 = L.q4(std::string(kAdapter) + ".0.weight", D, d * c.reshape_factor);
+        m.adapter2 = L.q4(std::string(kAdapter) + ".2.weight", D, D);
+        // ---- tied embeddings / lm_head: kept Q4 on device (WASM-path semantics, model.rs:689) ----
+        {
+            const GgufTensorInfo &t = L.info(kTokEmb);
+            VOX_CHECK(t.dtype == VOX_DTYPE_Q4_0, VOX_EFORMAT,
+                      "tok_embeddings must be Q4_0 in this build (got dtype %u)", t.dtype);
+            m.tok_emb = L.q4(kTokEmb, c.vocab, D);
+        }
+        // ---- decoder layers (loader.rs:329-375) ----
+        const int qd = c.dec_heads * c.dec_head_dim, kvd = c.dec_kv_heads * c.dec_head_dim;
+        m.dec.resize(c.dec_layers);
+        uint64_t dec_q4 = 0;
+        for (int j = 0; j < c.dec_layers; ++j) {
+            const std::string p = "layers." + std::to_string(j);
+            DecLayerW &l = m.dec[j];
+            const uint64_t before = L.q4_bytes;
+            l.ada0 = L.q4(p + ".ada_rms_norm_t_cond.0.weight", c.t_cond_dim, D);
+            l.ada2 = L.q4(p + ".ada_rms_norm_t_cond.2.weight", D, c.t_cond_dim);
+            l.attn_norm = L.f32_dev(p + ".attention_norm.weight", {D});
+            l.ffn_norm = L.f32_dev(p + ".ffn_norm.weight", {D});
+            l.wqkv = L.q4_concat({p + ".attention.wq.weight", p + ".attention.wk.weight", p + ".attention.wv.weight"},
+                                 {qd, kvd, kvd}, D);
+            l.wo = L.q4(p + ".attention.wo.weight", D, qd);
+            l.w13 = L.q4_interleave(p + ".feed_forward.w1.weight", p + ".feed_forward.w3.weight", c.dec_ffn, D);
+            l.w2 = L.q4(p + ".feed_forward.w2.weight", D, c.dec_ffn);
+            dec_q4 += L.q4_bytes - before;
+        }
+        m.dec_norm = L.f32_dev(kFinalNorm, {D});
+        build_rope(m.arena, c.enc_head_dim, m.enc_rope_len, m.rope_theta, &m.enc_cos, &m.enc_sin);
+        build_rope(m.arena, c.dec_head_dim, m.dec_rope_len, m.rope_theta, &m.dec_cos, &m.dec_sin);
+        m.mel.build(m.arena);
+        c.q4_bytes = L.q4_bytes;
+        c.device_bytes = m.arena.total;
+        c.decode_step_bytes = dec_q4 + m.tok_emb.bytes();
+        CUDA_OK(cudaDeviceSynchronize());
+    } catch (...) {
+        delete mp;
+        throw;
+    }
+    return mp;
+}
+
+// ======================================================================================
+// Session
+// ======================================================================================
+static int conv_out(int t) { return (t + 2 - 3) / 2 + 1; }  // conv.rs:47-48
+
+Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
+    VOX_CHECK(max_batch >= 1 && max_batch <= 64, VOX_EINVAL, "max_batch %d out of range [1,64]", max_batch);
+    VOX_CHECK(max_mel_frames >= 16, VOX_EINVAL, "max_mel_frames %d too small", max_mel_frames);
+    CUDA_OK(cudaSetDevice(m->device));
+    Session *s = new Session();
+    try {
+        const vox_model_info &c = m->info;
+        s->m = m;
+        s->arena.device = m->device;
+        s->max_batch = max_batch;
+        s->max_mel_frames = max_mel_frames;
+        s->T1_max = conv_out(max_mel_frames);
+        s->S_max = conv_out(s->T1_max);
+        s->S4_max = s->S_max / c.reshape_factor;
+        s->M_max = std::max(c.prefix_len, 64);
+        VOX_CHECK(s->S_max <= m->enc_rope_len, VOX_EINVAL, "max_mel_frames %d exceeds the encoder RoPE table", max_mel_frames);
+        CUDA_OK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+        for (auto &e : s->ev) CUDA_OK(cudaEventCreate(&e));
+        const size_t B = max_batch;
+        const int hdq = c.enc_heads * c.enc_head_dim;
+        s->mel = s->arena.alloc_n<float>(B * c.n_mels * max_mel_frames);
+        s->peak_scale = s->arena.alloc_n<float>(B);
+        s->h1 = s->arena.alloc_n<float>(B * s->T1_max * c.enc_dim);
+        const size_t rows = B * s->S_max;
+        s->x_enc = s->arena.alloc_n<float>(rows * c.enc_dim);
+        s->h_enc = s->arena.alloc_n<float>(rows * c.enc_dim);
+        s->qkv_enc = s->arena.alloc_n<float>(rows * 3 * hdq);
+        s->attn_enc = s->arena.alloc_n<float>(rows * hdq);
+        s->act_enc = s->arena.alloc_n<float>(rows * c.enc_ffn);
+        const size_t rows4 = B * std::max(s->S4_max, 1);
+        s->packed = s->arena.alloc_n<float>(rows4 * c.enc_dim * c.reshape_factor);
+        s->adapter_h = s->arena.alloc_n<float>(rows4 * c.dec_dim);
+        s->audio = s->arena.alloc_n<float>(rows4 * c.dec_dim);
+        // decoder
+        const int kv_cap = std::max(s->S4_max, s->M_max) + s->M_max;  // room for the incremental API
+        s->out_ld = kv_cap;
+        const size_t kv_elems = (size_t)c.dec_layers * B * c.dec_kv_heads * kv_cap * c.dec_head_dim;
+        s->kc = s->arena.alloc_n<float>(kv_elems);
+        s->vc = s->arena.alloc_n<float>(kv_elems);
+        const size_t drows = B * s->M_max;
+        const int qkvd = (c.dec_heads + 2 * c.dec_kv_heads) * c.dec_head_dim;
+        s->x_dec = s->arena.alloc_n<float>(drows * c.dec_dim);
+        s->h_dec = s->arena.alloc_n<float>(drows * c.dec_dim);
+        s->qkv_dec = s->arena.alloc_n<float>(drows * qkvd);
+        s->attn_dec = s->arena.alloc_n<float>(drows * c.dec_heads * c.dec_head_dim);
+        s->act_dec = s->arena.alloc_n<float>(drows * c.dec_ffn);
+        s->last_h = s->arena.alloc_n<float>(B * c.dec_dim);
+        s->logits = s->arena.alloc_n<float>(B * c.vocab);
+        s->ada = s->arena.alloc_n<float>((size_t)c.dec_layers * c.dec_dim);
+        s->t_embed = s->arena.alloc_n<float>(c.dec_dim);
+        s->ada_tmp = s->arena.alloc_n<float>(c.t_cond_dim);
+        s->d_pos = s->arena.alloc_n<int>(1);
+        s->d_outpos = s->arena.alloc_n<int>(1);
+        s->d_tok = s->arena.alloc_n<int>(B);
+        s->d_ids = s->arena.alloc_n<int>(drows);
+        s->d_out = s->arena.alloc_n<int>(B * s->out_ld);
+        CUDA_OK(cudaMemset(s->d_pos, 0, sizeof(int)));
+        CUDA_OK(cudaMemset(s->d_outpos, 0, sizeof(int)));
+        s->set_delay(6.0f);  // CLI default --delay 6 (transcribe.rs:49-51)
+    } catch (...) {
+        delete s;
+        throw;
+    }
+    return s;
+}
+
+Session::~Session() {
+    if (step_graph) cudaGraphExecDestroy(step_graph);
+    for (auto &e : ev)
+        if (e) cudaEventDestroy(e);
+    if (st) cudaStreamDestroy(st);
+}
+
+void Session::linear(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias,
+                     const float *res, int epi) {
+    if (M <= 8) launch_q4_matvec(w, x, M, y, ldy, bias, res, epi, st);
+    else launch_q4_gemm(w, x, M, y, ldy, bias, res, epi, st);
+}
+
+// TimeEmbedding::embed (time_embedding.rs:41-71) + the per-layer ADA scale
+// 1 + w2(gelu(w0(t)))  (model.rs:250-255), computed once: t is constant for a session.
+void Session::set_delay(float delay) {
+    const vox_model_info &c = m->info;
+    CUDA_OK(cudaSetDevice(m->device));
+    std::vector<float> t(c.dec_dim);
+    time_embedding(delay, c.dec_dim, t.data());
+    CUDA_OK(cudaMemcpyAsync(t_embed, t.data(), sizeof(float) * c.dec_dim, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<float> ones(c.dec_dim, 1.0f);
+    for (int j = 0; j < c.dec_layers; ++j) {
+        float *dst = ada + (size_t)j * c.dec_dim;
+        CUDA_OK(cudaMemcpyAsync(dst, ones.data(), sizeof(float) * c.dec_dim, cudaMemcpyHostToDevice, st));
+        launch_q4_matvec(m->dec[j].ada0, t_embed, 1, ada_tmp, c.t_cond_dim, nullptr, nullptr, EPI_GELU, st);
+        // dst = 1 + w2 . gelu(...)   (residual epilogue onto the vector of ones)
+        launch_q4_matvec(m->dec[j].ada2, ada_tmp, 1, dst, c.dec_dim, nullptr, dst, EPI_RESIDUAL, st);
+    }
+    CUDA_OK(cudaStreamSynchronize(st));
+    delay_set = true;
+}
+
+// Q4VoxtralModel::encode_audio (model.rs:783-788): conv -> 32 layers -> norm -> reshape x4 -> adapter
+void Session::encode(int B, int T) {
+    const vox_model_info &c = m->info;
+    VOX_CHECK(B >= 1 && B <= max_batch, VOX_EINVAL, "batch %d exceeds session max_batch %d", B, max_batch);
+    VOX_CHECK(T >= 1 && T <= max_mel_frames, VOX_EINVAL, "mel frames %d exceed session max_mel_frames %d", T, max_mel_frames);
+    const int T1 = conv_out(T), S = conv_out(T1), S4 = S / c.reshape_factor;
+    const int d = c.enc_dim, hdq = c.enc_heads * c.enc_head_dim;
+    const int rows = B * S;
+    launch_conv1(mel, m->conv1_w, m->conv1_b, h1, B, c.n_mels, T, T1, d, st);
+    launch_conv2_gemm(h1, m->conv2_w, m->conv2_b, x_enc, B, T1, S, d, d, st);
+    if (debug_capture && dbg_conv) CUDA_OK(cudaMemcpyAsync(dbg_conv, x_enc, sizeof(float) * rows * d, cudaMemcpyDeviceToDevice, st));
+    const float scale = powf((float)c.enc_head_dim, -0.5f);
+    for (int i = 0; i < c.enc_layers; ++i) {
+        const EncLayerW &l = m->enc[i];
+        launch_rmsnorm(x_enc, l.attn_norm, nullptr, h_enc, rows, d, m->norm_eps, st);
+        linear(l.wqkv, h_enc, rows, qkv_enc, 3 * hdq, l.bqkv, nullptr, EPI_NONE);
+        launch_rope_inplace(qkv_enc, rows, 3 * hdq, 0, c.enc_heads, hdq, c.enc_heads, c.enc_head_dim, S, 0,
+                            m->enc_cos, m->enc_sin, st);
+        launch_enc_attention(qkv_enc, attn_enc, B, S, c.enc_heads, c.enc_head_dim, 3 * hdq, 0, hdq, 2 * hdq,
+                             c.enc_window, scale, st);
+        linear(l.wo, attn_enc, rows, x_enc, d, l.bo, x_enc, EPI_RESIDUAL);
+        launch_rmsnorm(x_enc, l.ffn_norm, nullptr, h_enc, rows, d, m->norm_eps, st);
+        linear(l.w13, h_enc, rows, act_enc, c.enc_ffn, nullptr, nullptr, EPI_SILU_MUL);
+        linear(l.w2, act_enc, rows, x_enc, d, l.b2, x_enc, EPI_RESIDUAL);
+        if (debug_capture && dbg_layers)
+            CUDA_OK(cudaMemcpyAsync(dbg_layers + (size_t)i * rows * d, x_enc, sizeof(float) * rows * d,
+                                    cudaMemcpyDeviceToDevice, st));
+    }
+    launch_rmsnorm(x_enc, m->enc_norm, nullptr, h_enc, rows, d, m->norm_eps, st);
+    cur_B = B;
+    cur_S = S;
+    cur_S4 = S4;
+    if (S4 > 0) {
+        launch_reshape_rows(h_enc, packed, B, S, S4, d, c.reshape_factor, st);
+        linear(m->adapter0, packed, B * S4, adapter_h, c.dec_dim, nullptr, nullptr, EPI_GELU);
+        linear(m->adapter2, adapter_h, B * S4, audio, c.dec_dim, nullptr, nullptr, EPI_NONE);
+    }
+}
+
+// Q4LanguageModel::forward_hidden_with_cache (model.rs:665-677) over x_dec [B*M][D]; positions
+// *d_pos + i.  Leaves the final-normed hidden states in h_dec.  Does not advance *d_pos.
+void Session::decoder_forward(int B, int M) {
+    const vox_model_info &c = m->info;
+    const int D = c.dec_dim, H = c.dec_heads, Hkv = c.dec_kv_heads, hd = c.dec_head_dim;
+    const int qkvd = (H + 2 * Hkv) * hd, rows = B * M;
+    const float scale = powf((float)hd, -0.5f);
+    const size_t layer_stride = (size_t)max_batch * Hkv * out_ld * hd;
+    for (int j = 0; j < c.dec_layers; ++j) {
+        const DecLayerW &l = m->dec[j];
+        float *kcl = kc + (size_t)j * layer_stride, *vcl = vc + (size_t)j * layer_stride;
+        launch_rmsnorm(x_dec, l.attn_norm, nullptr, h_dec, rows, D, m->norm_eps, st);
+        linear(l.wqkv, h_dec, rows, qkv_dec, qkvd, nullptr, nullptr, EPI_NONE);
+        launch_dec_rope_append(qkv_dec, B, M, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, m->dec_cos, m->dec_sin, st);
+        launch_dec_attention(qkv_dec, B, M, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, c.dec_window, scale, attn_dec, st);
+        linear(l.wo, attn_dec, rows, x_dec, D, nullptr, x_dec, EPI_RESIDUAL);
+        launch_rmsnorm(x_dec, l.ffn_norm, ada + (size_t)j * D, h_dec, rows, D, m->norm_eps, st);
+        linear(l.w13, h_dec, rows, act_dec, c.dec_ffn, nullptr, nullptr, EPI_SILU_MUL);
+        linear(l.w2, act_dec, rows, x_dec, D, nullptr, x_dec, EPI_RESIDUAL);
+    }
+    launch_rmsnorm(x_dec, m->dec_norm, nullptr, h_dec, rows, D, m->norm_eps, st);
+}
+
+// One autoregressive step for B streams (model.rs:938-960): embed(prev token) + audio[pos-1],
+// 26 layers, lm_head, argmax, device-side feedback; all positions read from device counters.
+void Session::decode_step(int B) {
+    const vox_model_info &c = m->info;
+    launch_embed(m->tok_emb, d_tok, audio, cur_S4, B, 1, d_pos, x_dec, st);
+    decoder_forward(B, 1);
+    linear(m->tok_emb, h_dec, B, logits, c.vocab, nullptr, nullptr, EPI_NONE);
+    launch_argmax(logits, B, c.vocab, d_tok, d_out, out_ld, d_outpos, st);
+    launch_advance(d_pos, 1, d_outpos, 1, st);
+}
+
+void Session::reset() {
+    CUDA_OK(cudaMemsetAsync(d_pos, 0, sizeof(int), st));
+    CUDA_OK(cudaMemsetAsync(d_outpos, 0, sizeof(int), st));
+    cache_len = 0;
+}
+
+// Q4VoxtralModel::transcribe_streaming (model.rs:873-963).  Expects the mel in s->mel; records
+// ev[1] (after encode) and ev[2] (after decode) on the stream.  Returns tokens per stream.
+int Session::transcribe_from_mel(int B, int T, int32_t *out_ids, size_t cap_ids, vox_timings *tm, bool timed_pre) {
+    const vox_model_info &c = m->info;
+    (void)timed_pre;
+    encode(B, T);
+    CUDA_OK(cudaEventRecord(ev[2], st));
+    const int S4 = cur_S4, P = c.prefix_len;
+    int n_out = 0;
+    if (S4 >= P) {
+        n_out = S4 - P;
+        VOX_CHECK(cap_ids >= (size_t)B * n_out, VOX_ECAPACITY, "out_ids capacity %zu < %d x %d", cap_ids, B, n_out);
+        reset();
+        // prefix = [BOS] + [STREAMING_PAD]*37 (model.rs:883-892)
+        std::vector<int> prefix((size_t)B * P, 32);
+        for (int b = 0; b < B; ++b) prefix[(size_t)b * P] = 1;
+        CUDA_OK(cudaMemcpyAsync(d_ids, prefix.data(), sizeof(int) * prefix.size(), cudaMemcpyHostToDevice, st));
+        launch_embed(m->tok_emb, d_ids, audio, S4, B, P, d_pos, x_dec, st);
+        decoder_forward(B, P);
+        // lm_head on the last prefix row only (the reference computes all 38 rows and keeps one)
+        launch_gather_last(h_dec, last_h, B, P, c.dec_dim, st);
+        linear(m->tok_emb, last_h, B, logits, c.vocab, nullptr, nullptr, EPI_NONE);
+        launch_argmax(logits, B, c.vocab, d_tok, d_out, out_ld, d_outpos, st);
+        launch_advance(d_pos, P, d_outpos, 1, st);
+        const int steps = S4 - P - 1;
+        if (steps > 0) {
+            int done = 0;
+            if (use_graph) {
+                if (!step_graph || step_graph_B != B || step_graph_S4 != S4) {
+                    // first step eagerly (also performs any one-time kernel attribute setup),
+                    // then capture one step and replay it
+                    decode_step(B);
+                    done = 1;
+                    if (step_graph) { cudaGraphExecDestroy(step_graph); step_graph = nullptr; }
+                    if (steps > 1) {
+                        cudaGraph_t graph = nullptr;
+                        CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                        try {
+                            decode_step(B);
+                        } catch (...) {
+                            cudaStreamEndCapture(st, &graph);
+                            if (graph) cudaGraphDestroy(graph);
+                            throw;
+                        }
+                        CUDA_OK(cudaStreamEndCapture(st, &graph));
+                        cudaError_t e = cudaGraphInstantiate(&step_graph, graph, 0);
+                        cudaGraphDestroy(graph);
+                        cuda_check(e, "cudaGraphInstantiate");
+                        step_graph_B = B;
+                        step_graph_S4 = S4;
+                    }
+                }
+                for (; done < steps; ++done) CUDA_OK(cudaGraphLaunch(step_graph, st));
+            } else {
+                for (; done < steps; ++done) decode_step(B);
+            }
+        }
+    }
+    CUDA_OK(cudaEventRecord(ev[3], st));
+    std::vector<int> host((size_t)B * out_ld);
+    if (n_out > 0) CUDA_OK(cudaMemcpyAsync(host.data(), d_out, sizeof(int) * host.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < n_out; ++i) out_ids[(size_t)b * n_out + i] = host[(size_t)b * out_ld + i];
+    cache_len = n_out > 0 ? S4 - 1 : 0;
+    if (tm) {
+        tm->seq_len = S4;
+        tm->decode_tokens = n_out;
+    }
+    return n_out;
+}
+
+}  // namespace vox

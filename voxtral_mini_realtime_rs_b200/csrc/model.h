@@ -1,0 +1,129 @@
+// model.h -- Q4 Voxtral model resident in HBM + per-session state.
+// Mirrors Q4ModelLoader (reference src/gguf/loader.rs) and Q4VoxtralModel (src/gguf/model.rs).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "audio_host.h"
+#include "gguf.h"
+#include "kernels.h"
+
+namespace vox {
+
+void cuda_check(cudaError_t e, const char *what);
+#define CUDA_OK(x) ::vox::cuda_check((x), #x)
+
+// Owns device allocations of one device.
+struct DeviceArena {
+    int device = 0;
+    std::vector<void *> ptrs;
+    size_t total = 0;
+    void *alloc(size_t bytes);
+    template <typename T>
+    T *alloc_n(size_t n) { return (T *)alloc(n * sizeof(T)); }
+    template <typename T>
+    T *upload(const T *host, size_t n) {
+        T *d = alloc_n<T>(n);
+        CUDA_OK(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+        return d;
+    }
+    void release();
+    ~DeviceArena() { release(); }
+};
+
+// Mel constants on device (window + sparse filterbank).
+struct MelTables {
+    float *window = nullptr;
+    float *fb_vals = nullptr;
+    int *fb_start = nullptr, *fb_len = nullptr;
+    int fb_stride = 0;
+    std::vector<float> fb_dense, window_host;
+    void build(DeviceArena &arena);
+};
+
+struct EncLayerW {
+    float *attn_norm = nullptr, *ffn_norm = nullptr;
+    Q4Weight wqkv, wo, w13, w2;
+    float *bqkv = nullptr, *bo = nullptr, *b2 = nullptr;
+};
+struct DecLayerW {
+    float *attn_norm = nullptr, *ffn_norm = nullptr;
+    Q4Weight ada0, ada2, wqkv, wo, w13, w2;
+};
+
+struct Model {
+    int device = 0;
+    vox_model_info info{};
+    float rope_theta = 1e6f, norm_eps = 1e-5f;
+    DeviceArena arena;
+    // encoder
+    float *conv1_w = nullptr, *conv1_b = nullptr, *conv2_w = nullptr, *conv2_b = nullptr;
+    std::vector<EncLayerW> enc;
+    float *enc_norm = nullptr;
+    Q4Weight adapter0, adapter2, tok_emb;
+    std::vector<DecLayerW> dec;
+    float *dec_norm = nullptr;
+    float *enc_cos = nullptr, *enc_sin = nullptr, *dec_cos = nullptr, *dec_sin = nullptr;
+    int enc_rope_len = 4096, dec_rope_len = 16384;  // loader.rs:196, 284
+    MelTables mel;
+
+    static Model *load(const Gguf &g, int device);
+};
+
+// Repack raw GGUF Q4_0 blocks of one or more [N_i, K] matrices into the device layout.
+// interleave=true: two parts with equal N, rows (2i, 2i+1) = (a_i, b_i).
+Q4Weight upload_q4(DeviceArena &arena, const std::vector<const uint8_t *> &raw, const std::vector<int> &n_rows,
+                   int K, bool interleave);
+
+struct Session {
+    Model *m = nullptr;
+    int max_batch = 0, max_mel_frames = 0;
+    int T1_max = 0, S_max = 0, S4_max = 0, M_max = 0;
+    cudaStream_t st = nullptr;
+    DeviceArena arena;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // audio
+    float *pcm = nullptr, *pcm_pad = nullptr, *peak_scale = nullptr;
+    size_t pcm_cap = 0, pcm_pad_cap = 0;
+    float *mel = nullptr;
+    // encoder workspace
+    float *h1 = nullptr, *x_enc = nullptr, *h_enc = nullptr, *qkv_enc = nullptr, *attn_enc = nullptr, *act_enc = nullptr;
+    float *packed = nullptr, *adapter_h = nullptr, *audio = nullptr;
+    int cur_B = 0, cur_S = 0, cur_S4 = 0;
+    // decoder
+    float *kc = nullptr, *vc = nullptr;  // [L][B][Hkv][S4_max][hd]
+    float *x_dec = nullptr, *h_dec = nullptr, *qkv_dec = nullptr, *attn_dec = nullptr, *act_dec = nullptr;
+    float *last_h = nullptr, *logits = nullptr;
+    float *logits_all = nullptr;
+    size_t logits_all_cap = 0;
+    float *ada = nullptr, *t_embed = nullptr, *ada_tmp = nullptr;
+    bool delay_set = false;
+    int *d_pos = nullptr, *d_outpos = nullptr, *d_tok = nullptr, *d_ids = nullptr, *d_out = nullptr;
+    int out_ld = 0;
+    int cache_len = 0;  // host mirror of *d_pos for the incremental API
+    cudaGraphExec_t step_graph = nullptr;
+    int step_graph_B = 0, step_graph_S4 = 0;
+    bool use_graph = true;
+    std::vector<float> enc_debug;  // per-layer captures when debugging is enabled
+    bool debug_capture = false;
+    float *dbg_layers = nullptr;   // [enc_layers][B*S][enc_dim]
+    float *dbg_conv = nullptr;
+
+    static Session *create(Model *m, int max_batch, int max_mel_frames);
+    ~Session();
+    void set_delay(float delay);
+    // mel [B][128][T] already on device in s->mel
+    void encode(int B, int T);
+    void linear(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias, const float *res,
+                int epi);
+    void decoder_forward(int B, int M);
+    void decode_step(int B);
+    // runs prefill + loop; returns tokens per stream
+    int transcribe_from_mel(int B, int T, int32_t *out_ids, size_t cap_ids, vox_timings *tm, bool timed_pre);
+    void reset();
+};
+
+}  // namespace vox
