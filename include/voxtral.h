@@ -115,6 +115,12 @@ int32_t vox_dev_free(int32_t device, void *ptr_dev);
 int32_t vox_dev_upload(int32_t device, void *dst_dev, const void *src, size_t bytes);
 int32_t vox_dev_download(int32_t device, void *dst, const void *src_dev, size_t bytes);
 int32_t vox_dev_sync(int32_t device);
+/* cudaProfilerStart/Stop, for `ncu --profile-from-start off` captures of a region */
+int32_t vox_profiler_start(void);
+int32_t vox_profiler_stop(void);
+/* page-locked host memory for the end-to-end (host-buffer) path */
+int32_t vox_host_alloc_pinned(size_t bytes, void **ptr);
+int32_t vox_host_free_pinned(void *ptr);
 /* CUDA-event timing of `iters` back-to-back vox_q4_matmul launches cycling over `n_weights`
  * tensors (L2-defeating rotation); returns average ms per launch */
 int32_t vox_q4_matmul_bench(const vox_q4 *const *weights, int32_t n_weights, int32_t m,
@@ -144,6 +150,7 @@ typedef struct {
     float encode_ms;     /* conv + encoder + adapter              (e2e_bench.rs:161-167) */
     float decode_ms;     /* prefill + autoregressive loop         (e2e_bench.rs:170-232) */
     float total_ms;
+    float prefill_ms;    /* part of decode_ms: 38-token prefill + first argmax */
     int32_t decode_tokens; /* per stream: seq_len - 38 */
     int32_t seq_len;
 } vox_timings;

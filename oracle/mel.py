@@ -217,45 +217,5 @@ def time_embedding(t: float, dim: int = 3072, theta: float = 10000.0) -> np.ndar
 
 
 # ---------------------------------------------------------------- synthetic signals
-def sine_16k(seconds: float, freq: float = 440.0, amp: float = 0.5) -> np.ndarray:
-    """benches/audio.rs:13-18."""
-    n = int(seconds * SAMPLE_RATE)
-    i = np.arange(n, dtype=np.float64)
-    return (amp * np.sin(2.0 * math.pi * freq * i / SAMPLE_RATE)).astype(F32)
-
-
-def noise_chirp(seconds: float, seed: int = 1234) -> np.ndarray:
-    """Seeded N(0,1)*0.1 noise + linear chirp 100->4000 Hz."""
-    n = int(seconds * SAMPLE_RATE)
-    rng = np.random.Generator(np.random.PCG64(seed))
-    t = np.arange(n, dtype=np.float64) / SAMPLE_RATE
-    f0, f1 = 100.0, 4000.0
-    phase = 2.0 * math.pi * (f0 * t + 0.5 * (f1 - f0) * t * t / max(seconds, 1e-9))
-    x = 0.1 * rng.standard_normal(n) + 0.5 * np.sin(phase)
-    return x.astype(F32)
-
-
-def speechlike(seconds: float, seed: int = 1234) -> np.ndarray:
-    """Synthetic 'speech-like' test signal: 40-200 ms segments, each a mix of three random
-    sinusoids (80-5000 Hz) with a random envelope, ~15% silent gaps, plus a -40 dB noise
-    floor.  Gives a mel spectrogram that changes every few frames (no real audio is
-    available offline)."""
-    n = int(seconds * SAMPLE_RATE)
-    rng = np.random.Generator(np.random.PCG64(seed))
-    out = np.zeros(n, np.float64)
-    pos = 0
-    while pos < n:
-        seg = int(rng.uniform(0.04, 0.2) * SAMPLE_RATE)
-        end = min(n, pos + seg)
-        if rng.random() > 0.15:
-            t = np.arange(end - pos) / SAMPLE_RATE
-            amp = rng.uniform(0.05, 0.6)
-            sig = np.zeros(end - pos)
-            for _ in range(3):
-                f = math.exp(rng.uniform(math.log(80.0), math.log(5000.0)))
-                sig += rng.uniform(0.2, 1.0) * np.sin(2 * math.pi * f * t + rng.uniform(0, 2 * math.pi))
-            env = np.hanning(end - pos) ** 0.25
-            out[pos:end] = amp * sig * env / 3.0
-        pos = end
-    out += 0.003 * rng.standard_normal(n)
-    return out.astype(F32)
+# pure data generators, shared with bench.py
+from voxtral_mini_realtime_rs_b200.synth import noise_chirp, sine_16k, speechlike  # noqa: E402,F401

@@ -248,11 +248,13 @@ class OracleModel:
         cache = self.new_cache()
         hidden = self.decoder_forward_with_cache(x, ada, cache)
         margins = []
+        seconds = []
 
         def pick(hrow):
             logits = self.lm_head(hrow.reshape(1, -1))[0]
             top2 = torch.topk(logits, 2)
             margins.append(float(top2.values[0] - top2.values[1]))
+            seconds.append(int(top2.indices[1]))
             return int(torch.argmax(logits))          # lowest index on ties
 
         generated = prefix + [pick(hidden[PREFIX_LEN - 1])]
@@ -263,5 +265,6 @@ class OracleModel:
             generated.append(pick(hidden[0]))
         if info is not None:
             info["margins"] = margins
+            info["second"] = seconds
             info["audio_embeds"] = audio
         return generated[PREFIX_LEN:]

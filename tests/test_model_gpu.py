@@ -30,7 +30,7 @@ def test_mel_gpu_vs_oracle(vx):
     o = omel.MelSpectrogram()
     assert np.abs(ms.window() - o.window).max() < 1e-7
     fb, ofb = ms.mel_basis(), o.mel_basis
-    assert np.abs(fb - ofb).max() < 1e-6 * ofb.max() + 1e-9
+    assert np.abs(fb - ofb).max() < 2e-5 * ofb.max()
     for sig in (omel.sine_16k(1.0), omel.noise_chirp(3.0), omel.pad_audio(omel.speechlike(2.0)),
                 np.zeros(16000, np.float32), omel.speechlike(0.3)[:3333]):
         g = ms.compute_log(sig)

@@ -50,7 +50,7 @@ class _ModelInfo(C.Structure):
 
 class _Timings(C.Structure):
     _fields_ = [("preprocess_ms", C.c_float), ("encode_ms", C.c_float), ("decode_ms", C.c_float),
-                ("total_ms", C.c_float), ("decode_tokens", C.c_int32), ("seq_len", C.c_int32)]
+                ("total_ms", C.c_float), ("prefill_ms", C.c_float), ("decode_tokens", C.c_int32), ("seq_len", C.c_int32)]
 
 
 @dataclass
@@ -59,6 +59,7 @@ class Timings:
     encode_ms: float = 0.0
     decode_ms: float = 0.0
     total_ms: float = 0.0
+    prefill_ms: float = 0.0
     decode_tokens: int = 0
     seq_len: int = 0
 
@@ -103,6 +104,10 @@ _SIGS = {
     "vox_dev_upload": (C.c_int32, [C.c_int32, _P, _P, C.c_size_t]),
     "vox_dev_download": (C.c_int32, [C.c_int32, _P, _P, C.c_size_t]),
     "vox_dev_sync": (C.c_int32, [C.c_int32]),
+    "vox_profiler_start": (C.c_int32, []),
+    "vox_profiler_stop": (C.c_int32, []),
+    "vox_host_alloc_pinned": (C.c_int32, [C.c_size_t, C.POINTER(_P)]),
+    "vox_host_free_pinned": (C.c_int32, [_P]),
     "vox_q4_matmul_bench": (C.c_int32, [C.POINTER(_P), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_float)]),
     "vox_model_load_gguf": (C.c_int32, [C.c_char_p, C.c_int32, C.POINTER(_P)]),
@@ -380,6 +385,23 @@ class DeviceBuffer:
             self.free()
         except Exception:
             pass
+
+
+class PinnedArray:
+    """float32/int32 numpy view over page-locked host memory (cudaHostAlloc)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = _P()
+        _check(lib().vox_host_alloc_pinned(max(self.nbytes, 16), C.byref(self.ptr)))
+        buf = (C.c_char * max(self.nbytes, 16)).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().vox_host_free_pinned(self.ptr)
+            self.ptr = None
 
 
 class Q4Tensor:

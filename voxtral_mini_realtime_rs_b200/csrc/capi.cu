@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" boundary declared in include/voxtral.h.  Every entry point converts
 // exceptions into a status code + thread-local message; nothing here computes on the CPU on
 // behalf of the GPU path (no fallback): without a CUDA device the compute calls return VOX_ECUDA.
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 
 #include <cstring>
@@ -370,6 +371,28 @@ int32_t vox_dev_sync(int32_t device) {
     CUDA_OK(cudaDeviceSynchronize());
     VOX_API_END
 }
+int32_t vox_profiler_start(void) {
+    VOX_API_BEGIN
+    CUDA_OK(cudaProfilerStart());
+    VOX_API_END
+}
+int32_t vox_profiler_stop(void) {
+    VOX_API_BEGIN
+    CUDA_OK(cudaProfilerStop());
+    VOX_API_END
+}
+int32_t vox_host_alloc_pinned(size_t bytes, void **p) {
+    VOX_API_BEGIN
+    REQUIRE(p);
+    cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 16, cudaHostAllocDefault);
+    VOX_CHECK(e == cudaSuccess, VOX_ECUDA, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    VOX_API_END
+}
+int32_t vox_host_free_pinned(void *p) {
+    VOX_API_BEGIN
+    CUDA_OK(cudaFreeHost(p));
+    VOX_API_END
+}
 int32_t vox_q4_matmul_bench(const vox_q4 *const *ws, int32_t n_w, int32_t m, int32_t iters, int32_t warmup, float *avg_ms) {
     VOX_API_BEGIN
     REQUIRE(ws); REQUIRE(avg_ms);
@@ -475,7 +498,9 @@ int32_t vox_encode_audio(vox_session *sh, const float *mel, int32_t b, int32_t t
 
 static void fill_timings(Session *s, vox_timings *tm) {
     if (!tm) return;
-    float pre = 0, enc = 0, dec = 0;
+    float pre = 0, enc = 0, dec = 0, pf = 0;
+    CUDA_OK(cudaEventElapsedTime(&pf, s->ev[2], s->ev[4]));
+    tm->prefill_ms = pf;
     CUDA_OK(cudaEventElapsedTime(&pre, s->ev[0], s->ev[1]));
     CUDA_OK(cudaEventElapsedTime(&enc, s->ev[1], s->ev[2]));
     CUDA_OK(cudaEventElapsedTime(&dec, s->ev[2], s->ev[3]));

@@ -14,6 +14,7 @@ namespace vox {
 
 static std::atomic<uint64_t> g_launches{0};
 uint64_t kernel_launch_count() { return g_launches.load(); }
+void add_graph_launches(int64_t n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 static inline void post_launch(const char *name) {
     g_launches.fetch_add(1, std::memory_order_relaxed);

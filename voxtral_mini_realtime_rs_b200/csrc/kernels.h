@@ -86,5 +86,7 @@ void launch_peak_normalize_pad(const float *in, int B, size_t n, float target, i
                                size_t out_stride, size_t left, float *scale_buf, cudaStream_t st);
 
 uint64_t kernel_launch_count();
+// kernels executed through CUDA-graph replays (or, negative, captured-not-executed launches)
+void add_graph_launches(int64_t n);
 
 }  // namespace vox

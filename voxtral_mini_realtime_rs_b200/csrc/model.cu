@@ -535,6 +535,7 @@ int Session::transcribe_from_mel(int B, int T, int32_t *out_ids, size_t cap_ids,
         linear(m->tok_emb, last_h, B, logits, c.vocab, nullptr, nullptr, EPI_NONE);
         launch_argmax(logits, B, c.vocab, d_tok, d_out, out_ld, d_outpos, st);
         launch_advance(d_pos, P, d_outpos, 1, st);
+        CUDA_OK(cudaEventRecord(ev[4], st));
         const int steps = S4 - P - 1;
         if (steps > 0) {
             int done = 0;
@@ -547,6 +548,7 @@ int Session::transcribe_from_mel(int B, int T, int32_t *out_ids, size_t cap_ids,
                     if (step_graph) { cudaGraphExecDestroy(step_graph); step_graph = nullptr; }
                     if (steps > 1) {
                         cudaGraph_t graph = nullptr;
+                        const uint64_t before = kernel_launch_count();
                         CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
                         try {
                             decode_step(B);
@@ -556,6 +558,8 @@ int Session::transcribe_from_mel(int B, int T, int32_t *out_ids, size_t cap_ids,
                             throw;
                         }
                         CUDA_OK(cudaStreamEndCapture(st, &graph));
+                        step_graph_nodes = kernel_launch_count() - before;
+                        add_graph_launches(-(int64_t)step_graph_nodes);  // captured, not executed
                         cudaError_t e = cudaGraphInstantiate(&step_graph, graph, 0);
                         cudaGraphDestroy(graph);
                         cuda_check(e, "cudaGraphInstantiate");
@@ -563,12 +567,16 @@ int Session::transcribe_from_mel(int B, int T, int32_t *out_ids, size_t cap_ids,
                         step_graph_S4 = S4;
                     }
                 }
-                for (; done < steps; ++done) CUDA_OK(cudaGraphLaunch(step_graph, st));
+                for (; done < steps; ++done) {
+                    CUDA_OK(cudaGraphLaunch(step_graph, st));
+                    add_graph_launches((int64_t)step_graph_nodes);
+                }
             } else {
                 for (; done < steps; ++done) decode_step(B);
             }
         }
     }
+    if (S4 < P) CUDA_OK(cudaEventRecord(ev[4], st));
     CUDA_OK(cudaEventRecord(ev[3], st));
     std::vector<int> host((size_t)B * out_ld);
     if (n_out > 0) CUDA_OK(cudaMemcpyAsync(host.data(), d_out, sizeof(int) * host.size(), cudaMemcpyDeviceToHost, st));

@@ -84,7 +84,7 @@ struct Session {
     int T1_max = 0, S_max = 0, S4_max = 0, M_max = 0;
     cudaStream_t st = nullptr;
     DeviceArena arena;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     // audio
     float *pcm = nullptr, *pcm_pad = nullptr, *peak_scale = nullptr;
     size_t pcm_cap = 0, pcm_pad_cap = 0;
@@ -106,6 +106,7 @@ struct Session {
     int cache_len = 0;  // host mirror of *d_pos for the incremental API
     cudaGraphExec_t step_graph = nullptr;
     int step_graph_B = 0, step_graph_S4 = 0;
+    uint64_t step_graph_nodes = 0;
     bool use_graph = true;
     std::vector<float> enc_debug;  // per-layer captures when debugging is enabled
     bool debug_capture = false;
