@@ -49,6 +49,39 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+class RankReducer:
+    """max / sum of a scalar over the ranks of the (already initialised) process group; identity
+    at world size 1.  Device 'cpu' works with gloo (tests), 'cuda:<i>' with nccl (bench)."""
+
+    def __init__(self, dist_mod=None, device="cpu"):
+        self.dist, self.device = dist_mod, device
+
+    def _reduce(self, x: float, op_name: str) -> float:
+        if self.dist is None:
+            return float(x)
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op_name))
+        return float(t.item())
+
+    def max(self, x: float) -> float:
+        return self._reduce(x, "MAX")
+
+    def sum(self, x: float) -> float:
+        return self._reduce(x, "SUM")
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+
+def aggregate_throughput(red: RankReducer, local_tokens: int, local_seconds: float):
+    """Whole-job throughput: all ranks' tokens / the slowest rank's time (max over ranks)."""
+    total = red.sum(float(local_tokens))
+    t = red.max(float(local_seconds))
+    return total / t, total, t
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -185,25 +218,9 @@ def run_ours(args, rank, local_rank, world):
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    red = RankReducer(dist, f"cuda:{local_rank}")
+    barrier = red.barrier
+    max_over_ranks = red.max
 
     assert vx.device_count() > local_rank, "bench needs one CUDA device per rank (no CPU fallback)"
     ensure_gguf(rank, barrier)
@@ -242,11 +259,9 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     launches = model.launch_count() - launches0
     K = args.steps
-    dec_s = max_over_ranks(dec_ms / 1e3)
+    value, total_tokens, dec_s = aggregate_throughput(red, B * n_tok * K, dec_ms / 1e3)
     tot_s = max_over_ranks(tot_ms / 1e3)
     wall_s = max_over_ranks(wall)
-    total_tokens = world * B * n_tok * K
-    value = total_tokens / dec_s
     step_ms_loop = (dec_ms - pf_ms) / K / max(n_tok - 1, 1)   # one decode-step graph replay, this rank
 
     # ---- timed: end-to-end through the host-buffer C ABI (pinned PCM in, ids out)

@@ -100,6 +100,10 @@ def test_transcribe_streaming_token_parity(vx, tiny_model, tiny_oracle):
     tiny_model.debug("graph_off")
     assert tiny_model.transcribe_streaming(mel) == exp
     tiny_model.debug("graph_on")
+    # the SIMT matvec (tensor-core-assisted matvec disabled) gives the same ids
+    tiny_model.debug("tc_off")
+    assert tiny_model.transcribe_streaming(mel) == exp
+    tiny_model.debug("tc_on")
 
 
 def test_transcribe_short_audio_returns_empty(tiny_model):

@@ -16,6 +16,14 @@ from conftest import closed_form_weights
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["tc", "simt"])
+def matvec_mode(request, vx):
+    """Every test runs with both M<=8 kernels: tensor-core-assisted (default) and SIMT warp-reduce."""
+    assert vx.lib().vox_q4_set_matvec_mode(1 if request.param == "simt" else 0) == 0
+    yield request.param
+    vx.lib().vox_q4_set_matvec_mode(0)
+
+
 def _ref(x2d, raw, n, k, bias=None):
     return oq4.q4_matmul_c(x2d, raw, n, k, bias)
 

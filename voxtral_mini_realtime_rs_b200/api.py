@@ -99,6 +99,7 @@ _SIGS = {
     "vox_q4_matmul": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "vox_q4_matmul_host": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
     "vox_q4_tensor_free": (None, [_P]),
+    "vox_q4_set_matvec_mode": (C.c_int32, [C.c_int32]),
     "vox_dev_malloc": (C.c_int32, [C.c_int32, C.c_size_t, C.POINTER(_P)]),
     "vox_dev_free": (C.c_int32, [C.c_int32, _P]),
     "vox_dev_upload": (C.c_int32, [C.c_int32, _P, _P, C.c_size_t]),

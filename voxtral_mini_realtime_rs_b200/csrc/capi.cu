@@ -271,7 +271,7 @@ int32_t vox_q4_tensor_create(const uint8_t *bytes, size_t nbytes, int64_t n, int
     std::unique_ptr<vox_q4> q(new vox_q4());
     q->device = device;
     q->arena.device = device;
-    q->w = upload_q4(q->arena, {bytes}, {(int)n}, (int)k, false);
+    q->w = upload_q4(q->arena, {bytes}, {(int)n}, (int)k, false, true);
     *out = q.release();
     VOX_API_END
 }
@@ -303,9 +303,19 @@ int32_t vox_q4_tensor_dequantize(const vox_q4 *w, float *out) {
     }
     VOX_API_END
 }
+// 0 = tensor-core-assisted matvec for M <= 8 (default), 1 = SIMT warp-reduce matvec
+static int g_matvec_mode = (getenv("VOX_MATVEC") && std::string(getenv("VOX_MATVEC")) == "simt") ? 1 : 0;
 static void q4_matmul_dispatch(const Q4Weight &w, const float *x, float *y, int rows, const float *bias, cudaStream_t st) {
-    if (rows <= 8) launch_q4_matvec(w, x, rows, y, w.N, bias, nullptr, EPI_NONE, st);
+    const bool simt = g_matvec_mode == 1;
+    if (rows <= 8 && w.qs_tc && !simt) launch_q4_matvec_tc(w, x, rows, y, w.N, bias, nullptr, EPI_NONE, st);
+    else if (rows <= 8) launch_q4_matvec(w, x, rows, y, w.N, bias, nullptr, EPI_NONE, st);
     else launch_q4_gemm(w, x, rows, y, w.N, bias, nullptr, EPI_NONE, st);
+}
+int32_t vox_q4_set_matvec_mode(int32_t mode) {
+    VOX_API_BEGIN
+    VOX_CHECK(mode == 0 || mode == 1, VOX_EINVAL, "matvec mode must be 0 (tensor-core) or 1 (SIMT)");
+    g_matvec_mode = mode;
+    VOX_API_END
 }
 int32_t vox_q4_matmul(const vox_q4 *w, const float *x_dev, float *y_dev, int32_t b, int32_t m, const float *bias_dev,
                       void *stream) {
@@ -595,8 +605,8 @@ int32_t vox_generate_step_with_cache(vox_session *sh, const int32_t *ids, int32_
     }
     CUDA_OK(cudaMemcpyAsync(s->d_ids, ids, sizeof(int) * (size_t)b * m, cudaMemcpyHostToDevice, s->st));
     launch_embed(s->m->tok_emb, s->d_ids, nullptr, 0, b, m, nullptr, s->x_dec, s->st);
-    s->decoder_forward(b, m);
-    s->linear(s->m->tok_emb, s->h_dec, b * m, s->logits_all, c.vocab, nullptr, nullptr, EPI_NONE);
+    const bool pending = s->decoder_forward(b, m);
+    s->lm_head_rows(b * m, pending, s->logits_all);
     launch_advance(s->d_pos, m, nullptr, 0, s->st);
     CUDA_OK(cudaMemcpyAsync(logits, s->logits_all, sizeof(float) * n, cudaMemcpyDeviceToHost, s->st));
     CUDA_OK(cudaStreamSynchronize(s->st));
@@ -641,6 +651,11 @@ int32_t vox_session_debug_read(vox_session *sh, const char *what, float *out, si
         return VOX_OK;
     } else if (w == "graph_off") {
         s->use_graph = false;
+        if (n_floats) *n_floats = 0;
+        return VOX_OK;
+    } else if (w == "tc_off" || w == "tc_on") {
+        s->use_tc = (w == "tc_on");
+        if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
         if (n_floats) *n_floats = 0;
         return VOX_OK;
     } else if (w == "graph_on") {

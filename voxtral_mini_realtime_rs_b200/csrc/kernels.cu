@@ -22,6 +22,8 @@ static inline void post_launch(const char *name) {
     if (e != cudaSuccess) fail(VOX_ECUDA, fmt("%s launch failed: %s", name, cudaGetErrorString(e)));
 }
 
+void tc_count_launch(const char *name) { post_launch(name); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

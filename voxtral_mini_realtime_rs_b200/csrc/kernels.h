@@ -14,6 +14,9 @@ namespace vox {
 struct Q4Weight {
     const uint4 *qs = nullptr;   // [N][K/32]
     const __half *d = nullptr;   // [N][K/32]
+    // optional tensor-core ("TC") layout of the same blocks, see matvec_tc.cu
+    const uint4 *qs_tc = nullptr;  // [N/16][K/64][32]
+    const uint2 *d_tc = nullptr;   // [N/16][K/64][8]
     int N = 0, K = 0;
     size_t bytes() const { return (size_t)N * (K / 32) * 18; }
 };
@@ -28,6 +31,20 @@ enum Epi : int {
 // y[M,N] = x[M,K] . W^T, M <= 8 (decode / batched decode): warp-per-row-pair, shuffle reduce.
 void launch_q4_matvec(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias,
                       const float *res, int epi, cudaStream_t st);
+// same contract, dequant arithmetic on the tensor cores (mma.sync, f16 subnormal nibbles); needs the
+// TC layout (w.qs_tc).  matvec_tc.cu
+void launch_q4_matvec_tc(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias,
+                         const float *res, int epi, cudaStream_t st);
+// ... with the RMSNorm (+ optional ADA scale) of the input fused into the staging pass:
+// x := ((x / sqrt(mean(x^2)+eps)) * gamma) * ada
+void launch_q4_matvec_tc_norm(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias,
+                              const float *res, int epi, const float *gamma, const float *ada, float eps,
+                              cudaStream_t st);
+// single-token decoder attention fused with RoPE + KV append (decode_attn.cu); qkv rows [B][ld]
+bool dec_attn_fused_supported(int H, int Hkv, int hd);
+void launch_dec_attn_fused(float *qkv, int B, int ld, int H, int Hkv, int hd, float *kc, float *vc, int max_seq,
+                           const int *pos_ptr, int window, float scale, const float *cos_t, const float *sin_t,
+                           float *out, cudaStream_t st);
 // y[M,N] = A[M,K] . W^T for any M (encoder / prefill): tiled SIMT GEMM, in-tile dequant.
 void launch_q4_gemm(const Q4Weight &w, const float *a, int M, float *y, int ldy, const float *bias,
                     const float *res, int epi, cudaStream_t st);

@@ -58,8 +58,11 @@ void MelTables::build(DeviceArena &arena) {
     fb_len = arena.upload(len.data(), len.size());
 }
 
+static void build_tc_layout(DeviceArena &arena, Q4Weight &w, const std::vector<uint8_t> &qs,
+                            const std::vector<uint16_t> &ds);
+
 Q4Weight upload_q4(DeviceArena &arena, const std::vector<const uint8_t *> &raw, const std::vector<int> &n_rows,
-                   int K, bool interleave) {
+                   int K, bool interleave, bool tc_layout) {
     VOX_CHECK(K % 32 == 0, VOX_EINVAL, "Q4 weight with K=%d (not a multiple of 32)", K);
     const int bpr = K / 32;
     int N = 0;
@@ -86,7 +89,38 @@ Q4Weight upload_q4(DeviceArena &arena, const std::vector<const uint8_t *> &raw, 
     w.K = K;
     w.qs = (const uint4 *)arena.upload(qs.data(), qs.size());
     w.d = (const __half *)arena.upload(ds.data(), ds.size());
+    if (tc_layout) build_tc_layout(arena, w, qs, ds);
     return w;
+}
+
+// TC layout (matvec_tc.cu): tiles of 16 rows x pairs of blocks; lane (g,t) of a tile/pair owns word t
+// of rows g and g+8 of both blocks; scales grouped per g.  Rows / blocks beyond N / K are zero (d = 0).
+static void build_tc_layout(DeviceArena &arena, Q4Weight &w, const std::vector<uint8_t> &qs,
+                            const std::vector<uint16_t> &ds) {
+    const int bpr = w.K / 32;
+    const int n_tiles = (w.N + 15) / 16, n_pairs = (bpr + 1) / 2;
+    std::vector<uint32_t> q((size_t)n_tiles * n_pairs * 32 * 4, 0u);
+    std::vector<uint16_t> d((size_t)n_tiles * n_pairs * 8 * 4, 0);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(qs.data());
+    for (int T = 0; T < n_tiles; ++T)
+        for (int P = 0; P < n_pairs; ++P) {
+            uint32_t *qd = q.data() + ((size_t)T * n_pairs + P) * 128;
+            uint16_t *dd = d.data() + ((size_t)T * n_pairs + P) * 32;
+            for (int g = 0; g < 8; ++g)
+                for (int bb = 0; bb < 2; ++bb) {
+                    const int b = 2 * P + bb;
+                    if (b >= bpr) continue;
+                    for (int h = 0; h < 2; ++h) {
+                        const int row = 16 * T + g + 8 * h;
+                        if (row >= w.N) continue;
+                        const size_t blk = (size_t)row * bpr + b;
+                        for (int t = 0; t < 4; ++t) qd[(g * 4 + t) * 4 + bb * 2 + h] = src[blk * 4 + t];
+                        dd[g * 4 + bb * 2 + h] = ds[blk];
+                    }
+                }
+        }
+    w.qs_tc = (const uint4 *)arena.upload(q.data(), q.size());
+    w.d_tc = (const uint2 *)arena.upload(d.data(), d.size());
 }
 
 namespace {
@@ -159,20 +193,20 @@ struct Loader {
         q4_bytes += raw.size();
         return raw;
     }
-    Q4Weight q4(const std::string &name, int N, int K) {
+    Q4Weight q4(const std::string &name, int N, int K, bool tc = false) {
         std::vector<uint8_t> raw = q4_raw(name, N, K);
-        return upload_q4(m.arena, {raw.data()}, {N}, K, false);
+        return upload_q4(m.arena, {raw.data()}, {N}, K, false, tc);
     }
-    Q4Weight q4_concat(const std::vector<std::string> &names, const std::vector<int> &ns, int K) {
+    Q4Weight q4_concat(const std::vector<std::string> &names, const std::vector<int> &ns, int K, bool tc = false) {
         std::vector<std::vector<uint8_t>> raws;
         std::vector<const uint8_t *> ptrs;
         for (size_t i = 0; i < names.size(); ++i) raws.push_back(q4_raw(names[i], ns[i], K));
         for (auto &r : raws) ptrs.push_back(r.data());
-        return upload_q4(m.arena, ptrs, ns, K, false);
+        return upload_q4(m.arena, ptrs, ns, K, false, tc);
     }
-    Q4Weight q4_interleave(const std::string &a, const std::string &b, int N, int K) {
+    Q4Weight q4_interleave(const std::string &a, const std::string &b, int N, int K, bool tc = false) {
         std::vector<uint8_t> ra = q4_raw(a, N, K), rb = q4_raw(b, N, K);
-        return upload_q4(m.arena, {ra.data(), rb.data()}, {N, N}, K, true);
+        return upload_q4(m.arena, {ra.data(), rb.data()}, {N, N}, K, true, tc);
     }
     // optional bias (loader.rs:428-437): zeros when the tensor is absent
     std::vector<float> bias_or_zero(const std::string &name, int n) {
@@ -291,7 +325,7 @@ Model *Model::load(const Gguf &g, int device) {
             const GgufTensorInfo &t = L.info(kTokEmb);
             VOX_CHECK(t.dtype == VOX_DTYPE_Q4_0, VOX_EFORMAT,
                       "tok_embeddings must be Q4_0 in this build (got dtype %u)", t.dtype);
-            m.tok_emb = L.q4(kTokEmb, c.vocab, D);
+            m.tok_emb = L.q4(kTokEmb, c.vocab, D, true);
         }
         // ---- decoder layers (loader.rs:329-375) ----
         const int qd = c.dec_heads * c.dec_head_dim, kvd = c.dec_kv_heads * c.dec_head_dim;
@@ -306,10 +340,10 @@ Model *Model::load(const Gguf &g, int device) {
             l.attn_norm = L.f32_dev(p + ".attention_norm.weight", {D});
             l.ffn_norm = L.f32_dev(p + ".ffn_norm.weight", {D});
             l.wqkv = L.q4_concat({p + ".attention.wq.weight", p + ".attention.wk.weight", p + ".attention.wv.weight"},
-                                 {qd, kvd, kvd}, D);
-            l.wo = L.q4(p + ".attention.wo.weight", D, qd);
-            l.w13 = L.q4_interleave(p + ".feed_forward.w1.weight", p + ".feed_forward.w3.weight", c.dec_ffn, D);
-            l.w2 = L.q4(p + ".feed_forward.w2.weight", D, c.dec_ffn);
+                                 {qd, kvd, kvd}, D, true);
+            l.wo = L.q4(p + ".attention.wo.weight", D, qd, true);
+            l.w13 = L.q4_interleave(p + ".feed_forward.w1.weight", p + ".feed_forward.w3.weight", c.dec_ffn, D, true);
+            l.w2 = L.q4(p + ".feed_forward.w2.weight", D, c.dec_ffn, true);
             dec_q4 += L.q4_bytes - before;
         }
         m.dec_norm = L.f32_dev(kFinalNorm, {D});
@@ -407,7 +441,8 @@ Session::~Session() {
 
 void Session::linear(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias,
                      const float *res, int epi) {
-    if (M <= 8) launch_q4_matvec(w, x, M, y, ldy, bias, res, epi, st);
+    if (M <= 8 && w.qs_tc && use_tc) launch_q4_matvec_tc(w, x, M, y, ldy, bias, res, epi, st);
+    else if (M <= 8) launch_q4_matvec(w, x, M, y, ldy, bias, res, epi, st);
     else launch_q4_gemm(w, x, M, y, ldy, bias, res, epi, st);
 }
 
@@ -472,26 +507,58 @@ void Session::encode(int B, int T) {
 }
 
 // Q4LanguageModel::forward_hidden_with_cache (model.rs:665-677) over x_dec [B*M][D]; positions
-// *d_pos + i.  Leaves the final-normed hidden states in h_dec.  Does not advance *d_pos.
-void Session::decoder_forward(int B, int M) {
+// *d_pos + i.  Leaves the final-normed hidden states in h_dec -- or, on the fused decode path, returns
+// true and leaves the un-normed stream in x_dec for lm_head_rows().  Does not advance *d_pos.
+bool Session::decoder_forward(int B, int M) {
     const vox_model_info &c = m->info;
     const int D = c.dec_dim, H = c.dec_heads, Hkv = c.dec_kv_heads, hd = c.dec_head_dim;
     const int qkvd = (H + 2 * Hkv) * hd, rows = B * M;
     const float scale = powf((float)hd, -0.5f);
     const size_t layer_stride = (size_t)max_batch * Hkv * out_ld * hd;
+    // decode-sized problems: RMSNorm fused into the consuming matvec, RoPE + KV append fused into the
+    // attention kernel => 5 launches per layer instead of 8
+    const bool fused = use_tc && rows <= 8 && m->tok_emb.qs_tc != nullptr;
+    const bool fattn = fused && M == 1 && dec_attn_fused_supported(H, Hkv, hd);
     for (int j = 0; j < c.dec_layers; ++j) {
         const DecLayerW &l = m->dec[j];
         float *kcl = kc + (size_t)j * layer_stride, *vcl = vc + (size_t)j * layer_stride;
-        launch_rmsnorm(x_dec, l.attn_norm, nullptr, h_dec, rows, D, m->norm_eps, st);
-        linear(l.wqkv, h_dec, rows, qkv_dec, qkvd, nullptr, nullptr, EPI_NONE);
-        launch_dec_rope_append(qkv_dec, B, M, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, m->dec_cos, m->dec_sin, st);
-        launch_dec_attention(qkv_dec, B, M, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, c.dec_window, scale, attn_dec, st);
+        if (fused) {
+            launch_q4_matvec_tc_norm(l.wqkv, x_dec, rows, qkv_dec, qkvd, nullptr, nullptr, EPI_NONE, l.attn_norm, nullptr,
+                                     m->norm_eps, st);
+        } else {
+            launch_rmsnorm(x_dec, l.attn_norm, nullptr, h_dec, rows, D, m->norm_eps, st);
+            linear(l.wqkv, h_dec, rows, qkv_dec, qkvd, nullptr, nullptr, EPI_NONE);
+        }
+        if (fattn) {
+            launch_dec_attn_fused(qkv_dec, B, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, c.dec_window, scale, m->dec_cos,
+                                  m->dec_sin, attn_dec, st);
+        } else {
+            launch_dec_rope_append(qkv_dec, B, M, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, m->dec_cos, m->dec_sin, st);
+            launch_dec_attention(qkv_dec, B, M, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, c.dec_window, scale, attn_dec, st);
+        }
         linear(l.wo, attn_dec, rows, x_dec, D, nullptr, x_dec, EPI_RESIDUAL);
-        launch_rmsnorm(x_dec, l.ffn_norm, ada + (size_t)j * D, h_dec, rows, D, m->norm_eps, st);
-        linear(l.w13, h_dec, rows, act_dec, c.dec_ffn, nullptr, nullptr, EPI_SILU_MUL);
+        if (fused) {
+            launch_q4_matvec_tc_norm(l.w13, x_dec, rows, act_dec, c.dec_ffn, nullptr, nullptr, EPI_SILU_MUL, l.ffn_norm,
+                                     ada + (size_t)j * D, m->norm_eps, st);
+        } else {
+            launch_rmsnorm(x_dec, l.ffn_norm, ada + (size_t)j * D, h_dec, rows, D, m->norm_eps, st);
+            linear(l.w13, h_dec, rows, act_dec, c.dec_ffn, nullptr, nullptr, EPI_SILU_MUL);
+        }
         linear(l.w2, act_dec, rows, x_dec, D, nullptr, x_dec, EPI_RESIDUAL);
     }
-    launch_rmsnorm(x_dec, m->dec_norm, nullptr, h_dec, rows, D, m->norm_eps, st);
+    if (!fused) launch_rmsnorm(x_dec, m->dec_norm, nullptr, h_dec, rows, D, m->norm_eps, st);
+    return fused;
+}
+
+// lm_head over `rows` decoder rows (model.rs:680-691); `norm_pending`: x_dec still needs the final
+// RMSNorm (fused into the matvec), else h_dec already holds the normed hidden states.
+void Session::lm_head_rows(int rows, bool norm_pending, float *dst) {
+    const vox_model_info &c = m->info;
+    if (norm_pending)
+        launch_q4_matvec_tc_norm(m->tok_emb, x_dec, rows, dst, c.vocab, nullptr, nullptr, EPI_NONE, m->dec_norm, nullptr,
+                                 m->norm_eps, st);
+    else
+        linear(m->tok_emb, h_dec, rows, dst, c.vocab, nullptr, nullptr, EPI_NONE);
 }
 
 // One autoregressive step for B streams (model.rs:938-960): embed(prev token) + audio[pos-1],
@@ -499,8 +566,8 @@ void Session::decoder_forward(int B, int M) {
 void Session::decode_step(int B) {
     const vox_model_info &c = m->info;
     launch_embed(m->tok_emb, d_tok, audio, cur_S4, B, 1, d_pos, x_dec, st);
-    decoder_forward(B, 1);
-    linear(m->tok_emb, h_dec, B, logits, c.vocab, nullptr, nullptr, EPI_NONE);
+    const bool pending = decoder_forward(B, 1);
+    lm_head_rows(B, pending, logits);
     launch_argmax(logits, B, c.vocab, d_tok, d_out, out_ld, d_outpos, st);
     launch_advance(d_pos, 1, d_outpos, 1, st);
 }

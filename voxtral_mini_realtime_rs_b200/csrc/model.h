@@ -76,7 +76,7 @@ struct Model {
 // Repack raw GGUF Q4_0 blocks of one or more [N_i, K] matrices into the device layout.
 // interleave=true: two parts with equal N, rows (2i, 2i+1) = (a_i, b_i).
 Q4Weight upload_q4(DeviceArena &arena, const std::vector<const uint8_t *> &raw, const std::vector<int> &n_rows,
-                   int K, bool interleave);
+                   int K, bool interleave, bool tc_layout = false);
 
 struct Session {
     Model *m = nullptr;
@@ -108,6 +108,7 @@ struct Session {
     int step_graph_B = 0, step_graph_S4 = 0;
     uint64_t step_graph_nodes = 0;
     bool use_graph = true;
+    bool use_tc = true;  // tensor-core-assisted matvec for M <= 8 (VOX_MATVEC=simt disables)
     std::vector<float> enc_debug;  // per-layer captures when debugging is enabled
     bool debug_capture = false;
     float *dbg_layers = nullptr;   // [enc_layers][B*S][enc_dim]
@@ -120,7 +121,8 @@ struct Session {
     void encode(int B, int T);
     void linear(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias, const float *res,
                 int epi);
-    void decoder_forward(int B, int M);
+    bool decoder_forward(int B, int M);
+    void lm_head_rows(int rows, bool norm_pending, float *dst);
     void decode_step(int B);
     // runs prefill + loop; returns tokens per stream
     int transcribe_from_mel(int B, int T, int32_t *out_ids, size_t cap_ids, vox_timings *tm, bool timed_pre);
