@@ -13,3 +13,8 @@ print("value", d["value"], "e2e", d["e2e"]["value"], "stage_ms", d["stage_ms"])
 print("roofline", {k:d["roofline"][k] for k in ("achieved","frac","ms_per_launch")}, "single", d["roofline"]["single_stream"], "iso", d["roofline"]["isolated_matvec"])
 print("single_stream", d["single_stream"])
 PY
+echo "--- PDL off"
+VOX_PDL=0 timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('value', d['value'], 'roofline', d['roofline']['frac'], d['roofline']['ms_per_launch'], 'single', d['roofline']['single_stream'])"

@@ -22,6 +22,7 @@ void set_last_error(const std::string &m) { g_last_error = m; }
 }  // namespace vox
 
 using namespace vox;
+namespace vox { void set_tc_pdl(bool on); }
 
 #define VOX_API_BEGIN try {
 #define VOX_API_END                                \
@@ -651,6 +652,11 @@ int32_t vox_session_debug_read(vox_session *sh, const char *what, float *out, si
         return VOX_OK;
     } else if (w == "graph_off") {
         s->use_graph = false;
+        if (n_floats) *n_floats = 0;
+        return VOX_OK;
+    } else if (w == "pdl_off" || w == "pdl_on") {
+        set_tc_pdl(w == "pdl_on");
+        if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
         if (n_floats) *n_floats = 0;
         return VOX_OK;
     } else if (w == "tc_off" || w == "tc_on") {

@@ -29,6 +29,8 @@ dec_attn_fused_kernel(const float *__restrict__ qkv, const int ld, const int H, 
     __shared__ float kv[2][HD];
     __shared__ float red_m[DA_WARPS][G], red_l[DA_WARPS][G];
     __shared__ float red_acc[DA_WARPS][G][HD];
+    // let the next kernel (the wo matvec) start prefetching its weights while we run
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const int kvh = blockIdx.x, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pos = *pos_ptr;

@@ -754,6 +754,7 @@ void launch_dec_attention(const float *qkv, int B, int M, int ld, int H, int Hkv
 __global__ void embed_kernel(const uint4 *__restrict__ qs, const __half *__restrict__ ds, int K,
                              const int *__restrict__ ids, const float *__restrict__ audio, int audio_seq, int M,
                              const int *__restrict__ pos_ptr, float *__restrict__ x) {
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");  // PDL: next kernel may prefetch weights
     const int i = blockIdx.x, b = blockIdx.y;
     const int r = b * M + i;
     const int id = ids[r];
@@ -793,6 +794,7 @@ __global__ void argmax_kernel(const float *__restrict__ logits, int V, int *tok,
                               const int *__restrict__ out_pos_ptr) {
     __shared__ float sv[32];
     __shared__ int si[32];
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const int b = blockIdx.x;
     const float *row = logits + (size_t)b * V;
     float best = -INFINITY;
@@ -834,6 +836,7 @@ void launch_argmax(const float *logits, int B, int V, int *tok, int *out_ids, in
 }
 
 __global__ void advance_kernel(int *a, int da, int *b, int db) {
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     if (a) *a += da;
     if (b) *b += db;
 }

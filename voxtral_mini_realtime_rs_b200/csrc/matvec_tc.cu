@@ -40,8 +40,13 @@
 namespace vox {
 
 void tc_count_launch(const char *name);
+void set_tc_pdl(bool on);
 
 namespace {
+
+inline void cuda_check_tc(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) fail(VOX_ECUDA, fmt("CUDA error: %s: %s", what, cudaGetErrorString(e)));
+}
 
 constexpr int TC_WARPS = 8;
 constexpr int TC_THREADS = TC_WARPS * 32;
@@ -59,6 +64,37 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// Programmatic dependent launch: let the next kernel in the stream start its prologue (weight
+// prefetch) now; block until the previous kernel's results are visible.  No-ops when the kernel was
+// launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 
 struct NormArgs {
     const float *gamma;  // nullptr => no normalisation
@@ -141,16 +177,39 @@ __global__ void __launch_bounds__(TC_THREADS)
 q4_matvec_tc_kernel(const uint4 *__restrict__ qs_tc, const uint2 *__restrict__ d_tc, const int N, const int K,
                     const int n_tiles, const int n_pairs, const float *__restrict__ x, float *__restrict__ y,
                     const int ldy, const float *__restrict__ bias, const float *__restrict__ res,
-                    const int chunk_pairs, const NormArgs na) {
+                    const int chunk_pairs, const NormArgs na, const int nbuf) {
     constexpr int CG = (M + 3) / 4;  // column groups of 8 (= 4 tokens x 2 splits)
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float *sx = reinterpret_cast<float *>(smem_raw);                  // [0..7] scale, [8..15] 1/scale, [16..23] rms
     float *stat = sx + 24;                                            // [TC_WARPS][M][2] partial (ssq, amax)
     float *red = stat + TC_WARPS * M * 2;                             // [TC_WARPS][16 rows][M]
     float *off = red + TC_WARPS * 16 * M;                             // [chunk blocks][M]
     uint2 *bf = reinterpret_cast<uint2 *>(off + (size_t)chunk_pairs * 2 * M);  // [chunk blocks][2][2M][4]
+    // weight tiles arrive by TMA bulk copies: [nbuf][n_pairs*512 B nibbles | n_pairs*64 B scales]
+    const uint32_t tile_q_bytes = (uint32_t)n_pairs * 512u, tile_d_bytes = (uint32_t)n_pairs * 64u;
+    const uint32_t tile_bytes = tile_q_bytes + tile_d_bytes;
+    size_t woff = (size_t)(reinterpret_cast<unsigned char *>(bf + (size_t)chunk_pairs * 2 * 2 * 2 * M * 4) - smem_raw);
+    woff = (woff + 127) & ~(size_t)127;
+    unsigned char *wbuf = smem_raw + woff;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(wbuf + (size_t)nbuf * tile_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
+
+    auto issue_tile = [&](int tile, int buf) {  // one thread
+        mbar_expect_tx(&mbar[buf], tile_bytes);
+        bulk_g2s(wbuf + (size_t)buf * tile_bytes, qs_tc + (size_t)tile * n_pairs * 32, tile_q_bytes, &mbar[buf]);
+        bulk_g2s(wbuf + (size_t)buf * tile_bytes + tile_q_bytes, d_tc + (size_t)tile * n_pairs * 8, tile_d_bytes, &mbar[buf]);
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nbuf; ++i) mbar_init(&mbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    // the weights do not depend on the previous kernel: start streaming the first tile now, then let
+    // the next kernel begin its own prefetch, and only then wait for our input activations
+    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue_tile(blockIdx.x, 0);
+    pdl_trigger();
+    pdl_wait();
 
     // ---- pass 1: per-token sum of squares (for the fused RMSNorm) and max |x * gamma * ada|
     {
@@ -216,7 +275,18 @@ q4_matvec_tc_kernel(const uint4 *__restrict__ qs_tc, const uint2 *__restrict__ d
         __syncthreads();
     }
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = nbuf == 2 ? (it & 1) : 0;
+        const uint32_t parity = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+        const int next_tile = tile + gridDim.x;
+        if (nbuf == 2 && threadIdx.x == 0 && next_tile < n_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            issue_tile(next_tile, buf ^ 1);  // buffer buf^1 was released by the barrier ending iteration it-1
+        }
+        const uint4 *wq_s = reinterpret_cast<const uint4 *>(wbuf + (size_t)buf * tile_bytes);
+        const uint2 *wd_s = reinterpret_cast<const uint2 *>(wbuf + (size_t)buf * tile_bytes + tile_q_bytes);
+        mbar_wait(&mbar[buf], parity);
         float acc[CG][2];
 #pragma unroll
         for (int c = 0; c < CG; ++c) acc[c][0] = acc[c][1] = 0.0f;
@@ -229,8 +299,8 @@ q4_matvec_tc_kernel(const uint4 *__restrict__ qs_tc, const uint2 *__restrict__ d
                 tc_stage<M>(x, K, p0 * 2, np * 2, sx, sx + 16, na, bf, off);
                 __syncthreads();
             }
-            const uint4 *qp = qs_tc + ((size_t)tile * n_pairs + p0) * 32 + lane;
-            const uint2 *dp = d_tc + ((size_t)tile * n_pairs + p0) * 8 + g;
+            const uint4 *qp = wq_s + (size_t)p0 * 32 + lane;
+            const uint2 *dp = wd_s + (size_t)p0 * 8 + g;
             for (int pp0 = warp; pp0 < np; pp0 += TC_WARPS * TC_UNROLL) {
                 uint4 wq[TC_UNROLL];
                 uint2 wd[TC_UNROLL];
@@ -238,8 +308,8 @@ q4_matvec_tc_kernel(const uint4 *__restrict__ qs_tc, const uint2 *__restrict__ d
                 for (int u = 0; u < TC_UNROLL; ++u) {
                     const int pp = pp0 + u * TC_WARPS;
                     if (pp < np) {
-                        wq[u] = __ldg(qp + (size_t)pp * 32);
-                        wd[u] = __ldg(dp + (size_t)pp * 8);
+                        wq[u] = qp[(size_t)pp * 32];
+                        wd[u] = dp[(size_t)pp * 8];
                     }
                 }
 #pragma unroll
@@ -321,32 +391,63 @@ q4_matvec_tc_kernel(const uint4 *__restrict__ qs_tc, const uint2 *__restrict__ d
                 }
             }
         }
+        if (nbuf == 1 && next_tile < n_tiles) {
+            __syncthreads();  // everyone is done reading the single weight buffer
+            if (threadIdx.x == 0) {
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                issue_tile(next_tile, 0);
+            }
+        }
     }
 }
+
+// programmatic dependent launch between consecutive decode kernels (VOX_PDL=0 disables)
+bool g_tc_pdl = !(getenv("VOX_PDL") && getenv("VOX_PDL")[0] == '0');
 
 template <int M, int EPI>
 void tc_launch_t(const Q4Weight &w, const float *x, float *y, int ldy, const float *bias, const float *res,
                  const NormArgs &na, cudaStream_t st) {
-    constexpr size_t kBudget = 100 * 1024;
+    constexpr size_t kSmemMax = 200 * 1024;
     const int n_tiles = (w.N + 15) / 16;
     const int n_pairs = (w.K / 32 + 1) / 2;
+    const size_t tile_bytes = (size_t)n_pairs * 576;
     const size_t fixed = (24 + TC_WARPS * M * 2 + TC_WARPS * 16 * M) * sizeof(float);
     const size_t per_pair = 2 * ((size_t)M * sizeof(float) + (size_t)2 * 2 * M * 4 * sizeof(uint2));
-    int chunk_pairs = (int)((kBudget - fixed) / per_pair);
+    // activation staging budget: whatever is left beside one weight tile, capped at 100 KB
+    size_t budget = kSmemMax - tile_bytes - 256 - fixed;
+    if (budget > 100 * 1024) budget = 100 * 1024;
+    int chunk_pairs = (int)(budget / per_pair);
     if (chunk_pairs >= n_pairs) chunk_pairs = n_pairs;
     else chunk_pairs = (chunk_pairs / (TC_WARPS * TC_UNROLL)) * (TC_WARPS * TC_UNROLL);
-    VOX_CHECK(chunk_pairs > 0, VOX_EINVAL, "q4_matvec_tc: shared-memory budget too small");
-    const size_t smem = fixed + per_pair * chunk_pairs;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(q4_matvec_tc_kernel<M, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-        attr_set = true;
+    VOX_CHECK(chunk_pairs > 0, VOX_EINVAL, "q4_matvec_tc: shared-memory budget too small (K=%d, M=%d)", w.K, M);
+    const size_t act = fixed + per_pair * chunk_pairs;
+    // CTAs per SM by shared memory (one tile buffer), then decide whether a CTA sees several tiles
+    int per_sm = (int)((220 * 1024) / (act + tile_bytes + 256));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    int grid = n_tiles < 148 * per_sm ? n_tiles : 148 * per_sm;
+    int nbuf = 1;
+    if (n_tiles > grid && act + 2 * tile_bytes + 256 <= kSmemMax) nbuf = 2;
+    const size_t smem = act + 128 + (size_t)nbuf * tile_bytes + 64;
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        cuda_check_tc(cudaFuncSetAttribute(q4_matvec_tc_kernel<M, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(kSmemMax + 8 * 1024)),
+                      "cudaFuncSetAttribute(q4_matvec_tc)");
+        attr_set = kSmemMax + 8 * 1024;
     }
-    int grid = n_tiles;
-    const int cap = 148 * 16;
-    if (grid > cap) grid = cap;
-    q4_matvec_tc_kernel<M, EPI><<<grid, TC_THREADS, smem, st>>>(w.qs_tc, w.d_tc, w.N, w.K, n_tiles, n_pairs, x, y, ldy,
-                                                                bias, res, chunk_pairs, na);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_tc_pdl ? 1 : 0;
+    cuda_check_tc(cudaLaunchKernelEx(&cfg, q4_matvec_tc_kernel<M, EPI>, w.qs_tc, w.d_tc, w.N, w.K, n_tiles, n_pairs, x, y,
+                                     ldy, bias, res, chunk_pairs, na, nbuf),
+                  "cudaLaunchKernelEx(q4_matvec_tc)");
     tc_count_launch("q4_matvec_tc");
 }
 
@@ -363,6 +464,8 @@ void tc_launch_m(const Q4Weight &w, const float *x, float *y, int ldy, const flo
 }
 
 }  // namespace
+
+void set_tc_pdl(bool on) { g_tc_pdl = on; }
 
 void launch_q4_matvec_tc_norm(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias,
                               const float *res, int epi, const float *gamma, const float *ada, float eps,
