@@ -58,6 +58,7 @@ struct vox_q4 {
     Q4Weight w;
     float *x = nullptr, *y = nullptr, *bias = nullptr;  // scratch for the host-buffer call
     size_t x_cap = 0, y_cap = 0;
+    TcWork wk;  // split-K scratch of the tensor-core matvec (allocated with the tensor)
 };
 struct vox_model { Model *m; };
 struct vox_session { Session *s; };
@@ -273,6 +274,15 @@ int32_t vox_q4_tensor_create(const uint8_t *bytes, size_t nbytes, int64_t n, int
     q->device = device;
     q->arena.device = device;
     q->w = upload_q4(q->arena, {bytes}, {(int)n}, (int)k, false, true);
+    {   // split-K scratch: up to ceil(K/64/16) slices x 8 rows x padded N, and one ticket per row tile
+        const int n_tiles = (int)((n + 15) / 16), n_pairs = (int)((k / 32 + 1) / 2);
+        const size_t S = (size_t)(n_pairs + 15) / 16;
+        q->wk.partial_floats = S * 8 * (size_t)n_tiles * 16;
+        q->wk.partial = q->arena.alloc_n<float>(q->wk.partial_floats);
+        q->wk.n_counters = n_tiles;
+        q->wk.counters = q->arena.alloc_n<int>(n_tiles);
+        CUDA_OK(cudaMemset(q->wk.counters, 0, sizeof(int) * n_tiles));
+    }
     *out = q.release();
     VOX_API_END
 }
@@ -306,9 +316,11 @@ int32_t vox_q4_tensor_dequantize(const vox_q4 *w, float *out) {
 }
 // 0 = tensor-core-assisted matvec for M <= 8 (default), 1 = SIMT warp-reduce matvec
 static int g_matvec_mode = (getenv("VOX_MATVEC") && std::string(getenv("VOX_MATVEC")) == "simt") ? 1 : 0;
-static void q4_matmul_dispatch(const Q4Weight &w, const float *x, float *y, int rows, const float *bias, cudaStream_t st) {
+static void q4_matmul_dispatch(const Q4Weight &w, const float *x, float *y, int rows, const float *bias, cudaStream_t st,
+                               const TcWork *wk = nullptr) {
     const bool simt = g_matvec_mode == 1;
-    if (rows <= 8 && w.qs_tc && !simt) launch_q4_matvec_tc(w, x, rows, y, w.N, bias, nullptr, EPI_NONE, st);
+    if (rows <= 8 && w.qs_tc && !simt)
+        launch_q4_matvec_tc_ex(w, x, rows, y, w.N, bias, nullptr, EPI_NONE, nullptr, nullptr, 0.0f, wk, st);
     else if (rows <= 8) launch_q4_matvec(w, x, rows, y, w.N, bias, nullptr, EPI_NONE, st);
     else launch_q4_gemm(w, x, rows, y, w.N, bias, nullptr, EPI_NONE, st);
 }
@@ -324,7 +336,7 @@ int32_t vox_q4_matmul(const vox_q4 *w, const float *x_dev, float *y_dev, int32_t
     REQUIRE(w); REQUIRE(x_dev); REQUIRE(y_dev);
     VOX_CHECK(b > 0 && m > 0, VOX_EINVAL, "q4_matmul: B and M must be positive");
     CUDA_OK(cudaSetDevice(w->device));
-    q4_matmul_dispatch(w->w, x_dev, y_dev, b * m, bias_dev, (cudaStream_t)stream);
+    q4_matmul_dispatch(w->w, x_dev, y_dev, b * m, bias_dev, (cudaStream_t)stream, &w->wk);
     VOX_API_END
 }
 int32_t vox_q4_matmul_host(const vox_q4 *wc, const float *x, float *y, int32_t b, int32_t m, const float *bias) {
@@ -339,7 +351,7 @@ int32_t vox_q4_matmul_host(const vox_q4 *wc, const float *x, float *y, int32_t b
     if (bias && !w->bias) w->bias = w->arena.alloc_n<float>(w->w.N);
     CUDA_OK(cudaMemcpyAsync(w->x, x, sizeof(float) * xn, cudaMemcpyHostToDevice, 0));
     if (bias) CUDA_OK(cudaMemcpyAsync(w->bias, bias, sizeof(float) * w->w.N, cudaMemcpyHostToDevice, 0));
-    q4_matmul_dispatch(w->w, w->x, w->y, (int)rows, bias ? w->bias : nullptr, 0);
+    q4_matmul_dispatch(w->w, w->x, w->y, (int)rows, bias ? w->bias : nullptr, 0, &w->wk);
     CUDA_OK(cudaMemcpyAsync(y, w->y, sizeof(float) * yn, cudaMemcpyDeviceToHost, 0));
     CUDA_OK(cudaStreamSynchronize(0));
     VOX_API_END
@@ -605,7 +617,7 @@ int32_t vox_generate_step_with_cache(vox_session *sh, const int32_t *ids, int32_
         s->logits_all_cap = n;
     }
     CUDA_OK(cudaMemcpyAsync(s->d_ids, ids, sizeof(int) * (size_t)b * m, cudaMemcpyHostToDevice, s->st));
-    launch_embed(s->m->tok_emb, s->d_ids, nullptr, 0, b, m, nullptr, s->x_dec, s->st);
+    launch_embed(s->m->tok_emb, s->d_ids, nullptr, 0, b, m, nullptr, s->x_dec, s->fused_decode(b * m) ? s->ssq_x : nullptr, s->st);
     const bool pending = s->decoder_forward(b, m);
     s->lm_head_rows(b * m, pending, s->logits_all);
     launch_advance(s->d_pos, m, nullptr, 0, s->st);

@@ -753,7 +753,8 @@ void launch_dec_attention(const float *qkv, int B, int M, int ld, int H, int Hkv
 // =====================================================================================
 __global__ void embed_kernel(const uint4 *__restrict__ qs, const __half *__restrict__ ds, int K,
                              const int *__restrict__ ids, const float *__restrict__ audio, int audio_seq, int M,
-                             const int *__restrict__ pos_ptr, float *__restrict__ x) {
+                             const int *__restrict__ pos_ptr, float *__restrict__ x, float *__restrict__ ssq_out,
+                             const int rows_total) {
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");  // PDL: next kernel may prefetch weights
     const int i = blockIdx.x, b = blockIdx.y;
     const int r = b * M + i;
@@ -778,12 +779,22 @@ __global__ void embed_kernel(const uint4 *__restrict__ qs, const __half *__restr
         x[(size_t)r * K + k] = lo;
         x[(size_t)r * K + k + 16] = hi;
     }
+    if (ssq_out) {  // per-16-element sums of squares for the consumer's fused RMSNorm (fixed order)
+        __syncthreads();
+        for (int t = threadIdx.x; t < (K >> 4); t += blockDim.x) {
+            const float *p = x + (size_t)r * K + 16 * t;
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s = fmaf(p[j], p[j], s);
+            ssq_out[(size_t)t * rows_total + r] = s;
+        }
+    }
 }
 
 void launch_embed(const Q4Weight &emb, const int *ids, const float *audio, int audio_seq, int B, int M,
-                  const int *pos_ptr, float *x, cudaStream_t st) {
+                  const int *pos_ptr, float *x, float *ssq_out, cudaStream_t st) {
     dim3 grid(M, B);
-    embed_kernel<<<grid, 256, 0, st>>>(emb.qs, emb.d, emb.K, ids, audio, audio_seq, M, pos_ptr, x);
+    embed_kernel<<<grid, 256, 0, st>>>(emb.qs, emb.d, emb.K, ids, audio, audio_seq, M, pos_ptr, x, ssq_out, B * M);
     post_launch("embed");
 }
 
@@ -833,6 +844,69 @@ void launch_argmax(const float *logits, int B, int V, int *tok, int *out_ids, in
                    const int *out_pos_ptr, cudaStream_t st) {
     argmax_kernel<<<B, 1024, 0, st>>>(logits, V, tok, out_ids, out_ld, out_pos_ptr);
     post_launch("argmax");
+}
+
+__global__ void argmax_multi_kernel(const float *__restrict__ logits, int V, int *tok, int *out_ids, int out_ld,
+                                    const int *__restrict__ out_pos_ptr, float *svals, int *sidx, int *counters) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    __shared__ int is_last;
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    const int part = blockIdx.x, b = blockIdx.y;
+    const int per = (V + ARGMAX_PARTS - 1) / ARGMAX_PARTS;
+    const int i0 = part * per, i1 = min(V, i0 + per);
+    const float *row = logits + (size_t)b * V;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const float v = row[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+    auto combine = [](float &bv, int &bx, float ov, int ox) {
+        if (ov > bv || (ov == bv && ox < bx)) { bv = ov; bx = ox; }
+    };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) combine(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = blockDim.x >> 5;
+        best = threadIdx.x < nw ? sv[threadIdx.x] : -INFINITY;
+        bi = threadIdx.x < nw ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) combine(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+        if (threadIdx.x == 0) {
+            svals[b * ARGMAX_PARTS + part] = best;
+            sidx[b * ARGMAX_PARTS + part] = bi;
+            __threadfence();
+            const int old = atomicAdd(&counters[b], 1);
+            is_last = (old == ARGMAX_PARTS - 1);
+            if (is_last) counters[b] = 0;
+        }
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+        __threadfence();
+        best = -INFINITY;
+        bi = 0x7fffffff;
+        for (int p = threadIdx.x; p < ARGMAX_PARTS; p += 32)
+            combine(best, bi, __ldcg(svals + b * ARGMAX_PARTS + p), __ldcg(sidx + b * ARGMAX_PARTS + p));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) combine(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+        if (threadIdx.x == 0) {
+            if (bi == 0x7fffffff) bi = 0;
+            tok[b] = bi;
+            if (out_ids) out_ids[(size_t)b * out_ld + *out_pos_ptr] = bi;
+        }
+    }
+}
+
+void launch_argmax_multi(const float *logits, int B, int V, int *tok, int *out_ids, int out_ld,
+                         const int *out_pos_ptr, float *scratch_vals, int *scratch_idx, int *counters,
+                         cudaStream_t st) {
+    dim3 grid(ARGMAX_PARTS, B);
+    argmax_multi_kernel<<<grid, 256, 0, st>>>(logits, V, tok, out_ids, out_ld, out_pos_ptr, scratch_vals, scratch_idx, counters);
+    post_launch("argmax_multi");
 }
 
 __global__ void advance_kernel(int *a, int da, int *b, int db) {

@@ -35,6 +35,20 @@ void launch_q4_matvec(const Q4Weight &w, const float *x, int M, float *y, int ld
 // TC layout (w.qs_tc).  matvec_tc.cu
 void launch_q4_matvec_tc(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias,
                          const float *res, int epi, cudaStream_t st);
+// Session-owned scratch for the tensor-core matvec: split-K partial sums + tickets, and the per-tile
+// sums of squares that residual epilogues leave behind for the next kernel's fused RMSNorm.
+struct TcWork {
+    float *partial = nullptr;      // [S][M][n_tiles*16]
+    size_t partial_floats = 0;
+    int *counters = nullptr;       // [n_counters], zero between launches
+    int n_counters = 0;
+    const float *ssq_in = nullptr; // [ssq_in_parts][M] partial sums of squares of the input rows
+    int ssq_in_parts = 0;
+    float *ssq_out = nullptr;      // [N/16][M], written by EPI_RESIDUAL epilogues
+};
+void launch_q4_matvec_tc_ex(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias,
+                            const float *res, int epi, const float *gamma, const float *ada, float eps,
+                            const TcWork *wk, cudaStream_t st);
 // ... with the RMSNorm (+ optional ADA scale) of the input fused into the staging pass:
 // x := ((x / sqrt(mean(x^2)+eps)) * gamma) * ada
 void launch_q4_matvec_tc_norm(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias,
@@ -77,12 +91,19 @@ void launch_dec_attention(const float *qkv, int B, int M, int ld, int H, int Hkv
                           const float *vc, int max_seq, const int *pos_ptr, int window, float scale,
                           float *out, cudaStream_t st);
 // x[r][:] = (audio ? audio[b][*pos_ptr + i][:] : 0) + dequant(E[ids[r]]),  r = b*M + i
+// ssq_out (optional): [K/16][B*M] per-16-element sums of squares of the written rows (TcWork::ssq_in)
 void launch_embed(const Q4Weight &emb, const int *ids, const float *audio, int audio_seq, int B, int M,
-                  const int *pos_ptr, float *x, cudaStream_t st);
+                  const int *pos_ptr, float *x, float *ssq_out, cudaStream_t st);
 // greedy argmax (lowest index wins ties) over logits [B][V]; writes tok[b] and, if out_ids,
 // out_ids[b*out_ld + *out_pos_ptr]
 void launch_argmax(const float *logits, int B, int V, int *tok, int *out_ids, int out_ld,
                    const int *out_pos_ptr, cudaStream_t st);
+// multi-CTA variant: ARGMAX_PARTS CTAs per row, last one to arrive (atomic ticket) reduces the partial
+// results in fixed order; scratch: vals/idx [B][ARGMAX_PARTS], counters [B] zero between launches
+constexpr int ARGMAX_PARTS = 64;
+void launch_argmax_multi(const float *logits, int B, int V, int *tok, int *out_ids, int out_ld,
+                         const int *out_pos_ptr, float *scratch_vals, int *scratch_idx, int *counters,
+                         cudaStream_t st);
 // *a += da; *b += db  (device-side step counters for graph replay)
 void launch_advance(int *a, int da, int *b, int db, cudaStream_t st);
 // gather rows: dst[b][:] = src[b*M + (M-1)][:]

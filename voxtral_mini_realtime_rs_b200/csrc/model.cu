@@ -422,6 +422,32 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
         s->d_tok = s->arena.alloc_n<int>(B);
         s->d_ids = s->arena.alloc_n<int>(drows);
         s->d_out = s->arena.alloc_n<int>(B * s->out_ld);
+        {   // fused-decode scratch (see TcWork): sized for the largest split-K matvec at max_batch rows
+            const int mb = std::min(8, max_batch * 1);
+            size_t need = 0;
+            auto acc_need = [&](int N, int K) {
+                const int n_pairs = (K / 32 + 1) / 2;
+                const int S = (n_pairs + 15) / 16;  // worst case: 16 pairs per slice (M > 4)
+                need = std::max(need, (size_t)S * 8 * (size_t)((N + 15) / 16) * 16);
+            };
+            const int qkvd2 = (c.dec_heads + 2 * c.dec_kv_heads) * c.dec_head_dim;
+            acc_need(qkvd2, c.dec_dim);
+            acc_need(c.dec_dim, c.dec_heads * c.dec_head_dim);
+            acc_need(2 * c.dec_ffn, c.dec_dim);
+            acc_need(c.dec_dim, c.dec_ffn);
+            acc_need(c.vocab, c.dec_dim);
+            (void)mb;
+            s->tc_partial_floats = need;
+            s->tc_partial = s->arena.alloc_n<float>(need);
+            s->tc_n_counters = std::max((c.vocab + 15) / 16, (2 * c.dec_ffn + 15) / 16) + 16;
+            s->tc_counters = s->arena.alloc_n<int>(s->tc_n_counters);
+            CUDA_OK(cudaMemset(s->tc_counters, 0, sizeof(int) * s->tc_n_counters));
+            s->ssq_x = s->arena.alloc_n<float>((size_t)((c.dec_dim + 15) / 16) * 8);
+            s->am_vals = s->arena.alloc_n<float>((size_t)max_batch * ARGMAX_PARTS);
+            s->am_idx = s->arena.alloc_n<int>((size_t)max_batch * ARGMAX_PARTS);
+            s->am_cnt = s->arena.alloc_n<int>(max_batch);
+            CUDA_OK(cudaMemset(s->am_cnt, 0, sizeof(int) * max_batch));
+        }
         CUDA_OK(cudaMemset(s->d_pos, 0, sizeof(int)));
         CUDA_OK(cudaMemset(s->d_outpos, 0, sizeof(int)));
         s->set_delay(6.0f);  // CLI default --delay 6 (transcribe.rs:49-51)
@@ -509,6 +535,22 @@ void Session::encode(int B, int T) {
 // Q4LanguageModel::forward_hidden_with_cache (model.rs:665-677) over x_dec [B*M][D]; positions
 // *d_pos + i.  Leaves the final-normed hidden states in h_dec -- or, on the fused decode path, returns
 // true and leaves the un-normed stream in x_dec for lm_head_rows().  Does not advance *d_pos.
+bool Session::fused_decode(int rows) const { return use_tc && rows <= 8 && m->tok_emb.qs_tc != nullptr; }
+
+TcWork Session::tc_work(bool norm_in, bool ssq_out_) const {
+    TcWork w;
+    w.partial = tc_partial;
+    w.partial_floats = tc_partial_floats;
+    w.counters = tc_counters;
+    w.n_counters = tc_n_counters;
+    if (norm_in) {
+        w.ssq_in = ssq_x;
+        w.ssq_in_parts = (m->info.dec_dim + 15) / 16;
+    }
+    if (ssq_out_) w.ssq_out = ssq_x;
+    return w;
+}
+
 bool Session::decoder_forward(int B, int M) {
     const vox_model_info &c = m->info;
     const int D = c.dec_dim, H = c.dec_heads, Hkv = c.dec_kv_heads, hd = c.dec_head_dim;
@@ -517,14 +559,15 @@ bool Session::decoder_forward(int B, int M) {
     const size_t layer_stride = (size_t)max_batch * Hkv * out_ld * hd;
     // decode-sized problems: RMSNorm fused into the consuming matvec, RoPE + KV append fused into the
     // attention kernel => 5 launches per layer instead of 8
-    const bool fused = use_tc && rows <= 8 && m->tok_emb.qs_tc != nullptr;
+    const bool fused = fused_decode(rows);
+    const TcWork wk_norm = tc_work(true, false), wk_res = tc_work(false, true);
     const bool fattn = fused && M == 1 && dec_attn_fused_supported(H, Hkv, hd);
     for (int j = 0; j < c.dec_layers; ++j) {
         const DecLayerW &l = m->dec[j];
         float *kcl = kc + (size_t)j * layer_stride, *vcl = vc + (size_t)j * layer_stride;
         if (fused) {
-            launch_q4_matvec_tc_norm(l.wqkv, x_dec, rows, qkv_dec, qkvd, nullptr, nullptr, EPI_NONE, l.attn_norm, nullptr,
-                                     m->norm_eps, st);
+            launch_q4_matvec_tc_ex(l.wqkv, x_dec, rows, qkv_dec, qkvd, nullptr, nullptr, EPI_NONE, l.attn_norm, nullptr,
+                                   m->norm_eps, &wk_norm, st);
         } else {
             launch_rmsnorm(x_dec, l.attn_norm, nullptr, h_dec, rows, D, m->norm_eps, st);
             linear(l.wqkv, h_dec, rows, qkv_dec, qkvd, nullptr, nullptr, EPI_NONE);
@@ -536,15 +579,21 @@ bool Session::decoder_forward(int B, int M) {
             launch_dec_rope_append(qkv_dec, B, M, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, m->dec_cos, m->dec_sin, st);
             launch_dec_attention(qkv_dec, B, M, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, c.dec_window, scale, attn_dec, st);
         }
-        linear(l.wo, attn_dec, rows, x_dec, D, nullptr, x_dec, EPI_RESIDUAL);
+        if (fused)
+            launch_q4_matvec_tc_ex(l.wo, attn_dec, rows, x_dec, D, nullptr, x_dec, EPI_RESIDUAL, nullptr, nullptr, 0.f, &wk_res, st);
+        else
+            linear(l.wo, attn_dec, rows, x_dec, D, nullptr, x_dec, EPI_RESIDUAL);
         if (fused) {
-            launch_q4_matvec_tc_norm(l.w13, x_dec, rows, act_dec, c.dec_ffn, nullptr, nullptr, EPI_SILU_MUL, l.ffn_norm,
-                                     ada + (size_t)j * D, m->norm_eps, st);
+            launch_q4_matvec_tc_ex(l.w13, x_dec, rows, act_dec, c.dec_ffn, nullptr, nullptr, EPI_SILU_MUL, l.ffn_norm,
+                                   ada + (size_t)j * D, m->norm_eps, &wk_norm, st);
         } else {
             launch_rmsnorm(x_dec, l.ffn_norm, ada + (size_t)j * D, h_dec, rows, D, m->norm_eps, st);
             linear(l.w13, h_dec, rows, act_dec, c.dec_ffn, nullptr, nullptr, EPI_SILU_MUL);
         }
-        linear(l.w2, act_dec, rows, x_dec, D, nullptr, x_dec, EPI_RESIDUAL);
+        if (fused)
+            launch_q4_matvec_tc_ex(l.w2, act_dec, rows, x_dec, D, nullptr, x_dec, EPI_RESIDUAL, nullptr, nullptr, 0.f, &wk_res, st);
+        else
+            linear(l.w2, act_dec, rows, x_dec, D, nullptr, x_dec, EPI_RESIDUAL);
     }
     if (!fused) launch_rmsnorm(x_dec, m->dec_norm, nullptr, h_dec, rows, D, m->norm_eps, st);
     return fused;
@@ -554,9 +603,11 @@ bool Session::decoder_forward(int B, int M) {
 // RMSNorm (fused into the matvec), else h_dec already holds the normed hidden states.
 void Session::lm_head_rows(int rows, bool norm_pending, float *dst) {
     const vox_model_info &c = m->info;
-    if (norm_pending)
-        launch_q4_matvec_tc_norm(m->tok_emb, x_dec, rows, dst, c.vocab, nullptr, nullptr, EPI_NONE, m->dec_norm, nullptr,
-                                 m->norm_eps, st);
+    if (norm_pending) {
+        const TcWork wk = tc_work(true, false);
+        launch_q4_matvec_tc_ex(m->tok_emb, x_dec, rows, dst, c.vocab, nullptr, nullptr, EPI_NONE, m->dec_norm, nullptr,
+                               m->norm_eps, &wk, st);
+    }
     else
         linear(m->tok_emb, h_dec, rows, dst, c.vocab, nullptr, nullptr, EPI_NONE);
 }
@@ -565,10 +616,10 @@ void Session::lm_head_rows(int rows, bool norm_pending, float *dst) {
 // 26 layers, lm_head, argmax, device-side feedback; all positions read from device counters.
 void Session::decode_step(int B) {
     const vox_model_info &c = m->info;
-    launch_embed(m->tok_emb, d_tok, audio, cur_S4, B, 1, d_pos, x_dec, st);
+    launch_embed(m->tok_emb, d_tok, audio, cur_S4, B, 1, d_pos, x_dec, fused_decode(B) ? ssq_x : nullptr, st);
     const bool pending = decoder_forward(B, 1);
     lm_head_rows(B, pending, logits);
-    launch_argmax(logits, B, c.vocab, d_tok, d_out, out_ld, d_outpos, st);
+    launch_argmax_multi(logits, B, c.vocab, d_tok, d_out, out_ld, d_outpos, am_vals, am_idx, am_cnt, st);
     launch_advance(d_pos, 1, d_outpos, 1, st);
 }
 
@@ -595,7 +646,7 @@ int Session::transcribe_from_mel(int B, int T, int32_t *out_ids, size_t cap_ids,
         std::vector<int> prefix((size_t)B * P, 32);
         for (int b = 0; b < B; ++b) prefix[(size_t)b * P] = 1;
         CUDA_OK(cudaMemcpyAsync(d_ids, prefix.data(), sizeof(int) * prefix.size(), cudaMemcpyHostToDevice, st));
-        launch_embed(m->tok_emb, d_ids, audio, S4, B, P, d_pos, x_dec, st);
+        launch_embed(m->tok_emb, d_ids, audio, S4, B, P, d_pos, x_dec, fused_decode(B * P) ? ssq_x : nullptr, st);
         decoder_forward(B, P);
         // lm_head on the last prefix row only (the reference computes all 38 rows and keeps one)
         launch_gather_last(h_dec, last_h, B, P, c.dec_dim, st);

@@ -108,6 +108,17 @@ struct Session {
     int step_graph_B = 0, step_graph_S4 = 0;
     uint64_t step_graph_nodes = 0;
     bool use_graph = true;
+    // scratch of the fused decode path: split-K partials + tickets, per-tile sums of squares of the
+    // residual stream (consumed by the next kernel's fused RMSNorm), multi-CTA argmax scratch
+    float *tc_partial = nullptr;
+    size_t tc_partial_floats = 0;
+    int *tc_counters = nullptr;
+    int tc_n_counters = 0;
+    float *ssq_x = nullptr;
+    float *am_vals = nullptr;
+    int *am_idx = nullptr, *am_cnt = nullptr;
+    TcWork tc_work(bool norm_in, bool ssq_out) const;
+    bool fused_decode(int rows) const;
     bool use_tc = true;  // tensor-core-assisted matvec for M <= 8 (VOX_MATVEC=simt disables)
     std::vector<float> enc_debug;  // per-layer captures when debugging is enabled
     bool debug_capture = false;
