@@ -108,8 +108,9 @@ int32_t vox_q4_matmul(const vox_q4 *w, const float *x_dev, float *y_dev, int32_t
 int32_t vox_q4_matmul_host(const vox_q4 *w, const float *x, float *y, int32_t b, int32_t m,
                            const float *bias /* nullable */);
 void vox_q4_tensor_free(vox_q4 *w);
-/* kernel selection for M <= 8 of the operator seam: 0 = tensor-core-assisted matvec (default),
- * 1 = SIMT warp-reduce matvec.  Both implement the same contract; exposed for A/B measurement. */
+/* kernel selection of the operator seam (bit mask, default 0): bit 0 = SIMT warp-reduce matvec instead of
+ * the tensor-core-assisted one (M <= 8); bit 1 = SIMT tiled GEMM instead of the tcgen05 GEMM (M > 8).
+ * All implement the same contract; exposed for A/B measurement and parity tests. */
 int32_t vox_q4_set_matvec_mode(int32_t mode);
 
 /* small device-memory helpers so that non-CUDA callers (ctypes, Rust) can drive the *_dev calls */

@@ -18,8 +18,9 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True, params=["tc", "simt"])
 def matvec_mode(request, vx):
-    """Every test runs with both M<=8 kernels: tensor-core-assisted (default) and SIMT warp-reduce."""
-    assert vx.lib().vox_q4_set_matvec_mode(1 if request.param == "simt" else 0) == 0
+    """Every test runs with both kernel families: tensor-core paths (mma.sync matvec for M<=8, tcgen05
+    GEMM for M>8; default) and the SIMT matvec / SIMT tiled GEMM."""
+    assert vx.lib().vox_q4_set_matvec_mode(3 if request.param == "simt" else 0) == 0
     yield request.param
     vx.lib().vox_q4_set_matvec_mode(0)
 
@@ -111,6 +112,23 @@ def test_q4_matmul_all_m_random_blocks(vx, m):
     exp = _ref(x[0], raw, n, k, bias)
     scale = np.abs(exp).max()
     assert np.abs(out[0] - exp).max() < 2e-5 * scale + 1e-5
+
+
+@pytest.mark.parametrize("m,n,k", [(130, 256, 1280), (586, 1280, 2048), (38, 384, 3072), (257, 128, 64)])
+def test_q4_gemm_large_m_accuracy(vx, m, n, k):
+    """Encoder / prefill sized GEMMs (N % 128 == 0, K % 64 == 0 => tcgen05 path in 'tc' mode): the
+    3x2 bf16 split keeps f32-grade accuracy (error ~ f32 summation-order noise, far below 1e-3)."""
+    rng = np.random.default_rng(m + n)
+    raw = np.empty((n * k // 32, 18), np.uint8)
+    raw[:, :2] = rng.uniform(0.002, 0.02, n * k // 32).astype(np.float16).view(np.uint8).reshape(-1, 2)
+    raw[:, 2:] = rng.integers(0, 256, (n * k // 32, 16), dtype=np.uint8)
+    raw = raw.reshape(-1)
+    x = (rng.standard_normal((1, m, k)) * rng.uniform(0.1, 3.0, (1, m, 1))).astype(np.float32)
+    bias = rng.standard_normal(n).astype(np.float32)
+    out = vx.q4_matmul(x, vx.Q4Tensor.from_q4_bytes(raw, (n, k)), bias)
+    exp = _ref(x[0], raw, n, k, bias)
+    err = np.abs(out[0] - exp).max()
+    assert err < 3e-5 * np.abs(exp).max() + 1e-5, err
 
 
 def test_q4_matvec_k_chunked(vx):

@@ -59,6 +59,8 @@ struct vox_q4 {
     float *x = nullptr, *y = nullptr, *bias = nullptr;  // scratch for the host-buffer call
     size_t x_cap = 0, y_cap = 0;
     TcWork wk;  // split-K scratch of the tensor-core matvec (allocated with the tensor)
+    void *xt = nullptr;  // split tiles for the tcgen05 GEMM (M > 8)
+    size_t xt_elems = 0;
 };
 struct vox_model { Model *m; };
 struct vox_session { Session *s; };
@@ -317,8 +319,18 @@ int32_t vox_q4_tensor_dequantize(const vox_q4 *w, float *out) {
 // 0 = tensor-core-assisted matvec for M <= 8 (default), 1 = SIMT warp-reduce matvec
 static int g_matvec_mode = (getenv("VOX_MATVEC") && std::string(getenv("VOX_MATVEC")) == "simt") ? 1 : 0;
 static void q4_matmul_dispatch(const Q4Weight &w, const float *x, float *y, int rows, const float *bias, cudaStream_t st,
-                               const TcWork *wk = nullptr) {
-    const bool simt = g_matvec_mode == 1;
+                               const TcWork *wk = nullptr, vox_q4 *h = nullptr) {
+    const bool simt = (g_matvec_mode & 1) != 0;
+    if (rows > 8 && h && !(g_matvec_mode & 2) && gemm_tc5_supported(w, rows)) {
+        const size_t need = gemm_tc5_split_elems(rows, w.K);
+        if (need > h->xt_elems) {
+            h->xt = h->arena.alloc(need * 2);
+            h->xt_elems = need;
+        }
+        launch_split_tiles(x, rows, w.K, nullptr, nullptr, 0.0f, h->xt, st);
+        launch_q4_gemm_tc5(w, h->xt, rows, y, w.N, bias, nullptr, EPI_NONE, st);
+        return;
+    }
     if (rows <= 8 && w.qs_tc && !simt)
         launch_q4_matvec_tc_ex(w, x, rows, y, w.N, bias, nullptr, EPI_NONE, nullptr, nullptr, 0.0f, wk, st);
     else if (rows <= 8) launch_q4_matvec(w, x, rows, y, w.N, bias, nullptr, EPI_NONE, st);
@@ -326,7 +338,7 @@ static void q4_matmul_dispatch(const Q4Weight &w, const float *x, float *y, int 
 }
 int32_t vox_q4_set_matvec_mode(int32_t mode) {
     VOX_API_BEGIN
-    VOX_CHECK(mode == 0 || mode == 1, VOX_EINVAL, "matvec mode must be 0 (tensor-core) or 1 (SIMT)");
+    VOX_CHECK(mode >= 0 && mode <= 3, VOX_EINVAL, "mode bits: 1 = SIMT matvec (M<=8), 2 = SIMT GEMM (M>8)");
     g_matvec_mode = mode;
     VOX_API_END
 }
@@ -336,7 +348,7 @@ int32_t vox_q4_matmul(const vox_q4 *w, const float *x_dev, float *y_dev, int32_t
     REQUIRE(w); REQUIRE(x_dev); REQUIRE(y_dev);
     VOX_CHECK(b > 0 && m > 0, VOX_EINVAL, "q4_matmul: B and M must be positive");
     CUDA_OK(cudaSetDevice(w->device));
-    q4_matmul_dispatch(w->w, x_dev, y_dev, b * m, bias_dev, (cudaStream_t)stream, &w->wk);
+    q4_matmul_dispatch(w->w, x_dev, y_dev, b * m, bias_dev, (cudaStream_t)stream, &w->wk, const_cast<vox_q4 *>(w));
     VOX_API_END
 }
 int32_t vox_q4_matmul_host(const vox_q4 *wc, const float *x, float *y, int32_t b, int32_t m, const float *bias) {
@@ -351,7 +363,7 @@ int32_t vox_q4_matmul_host(const vox_q4 *wc, const float *x, float *y, int32_t b
     if (bias && !w->bias) w->bias = w->arena.alloc_n<float>(w->w.N);
     CUDA_OK(cudaMemcpyAsync(w->x, x, sizeof(float) * xn, cudaMemcpyHostToDevice, 0));
     if (bias) CUDA_OK(cudaMemcpyAsync(w->bias, bias, sizeof(float) * w->w.N, cudaMemcpyHostToDevice, 0));
-    q4_matmul_dispatch(w->w, w->x, w->y, (int)rows, bias ? w->bias : nullptr, 0, &w->wk);
+    q4_matmul_dispatch(w->w, w->x, w->y, (int)rows, bias ? w->bias : nullptr, 0, &w->wk, w);
     CUDA_OK(cudaMemcpyAsync(y, w->y, sizeof(float) * yn, cudaMemcpyDeviceToHost, 0));
     CUDA_OK(cudaStreamSynchronize(0));
     VOX_API_END
@@ -669,6 +681,10 @@ int32_t vox_session_debug_read(vox_session *sh, const char *what, float *out, si
     } else if (w == "pdl_off" || w == "pdl_on") {
         set_tc_pdl(w == "pdl_on");
         if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
+        if (n_floats) *n_floats = 0;
+        return VOX_OK;
+    } else if (w == "gemm_simt" || w == "gemm_tc") {
+        s->use_gemm_tc = (w == "gemm_tc");
         if (n_floats) *n_floats = 0;
         return VOX_OK;
     } else if (w == "tc_off" || w == "tc_on") {

@@ -1,0 +1,402 @@
+// gemm_tc5.cu -- K3: Q4_0 dequant-GEMM on the 5th-generation tensor cores (tcgen05 + TMEM) for
+// encoder / prefill sized problems:   Y[M_tok, N] = X[M_tok, K] . W[N, K]^T  (+ epilogue).
+// Reference arithmetic: src/gguf/shader_naive.wgsl:31-98 (w = (q-8)*d in f32, f32 accumulate).
+//
+// f32-grade accuracy on bf16 tensor cores ("3 x 2 split"): tcgen05 has no f32-input MMA, so
+//   w = w_hi + w_lo            exact: (q-8)*d has <= 15 significant bits = two bf16 pieces
+//   x = x_h + x_m + x_l        exact: 24 bits = three bf16 pieces
+// and the product is accumulated in f32 TMEM from the five largest terms
+//   w_hi x_h + w_hi x_m + w_lo x_h + w_hi x_l + w_lo x_m        (dropped: w_lo x_l ~ 2^-24 |w||x|)
+// i.e. 5 kind::f16 MMAs per 16-wide K step.  Measured against the oracle in tests/.
+//
+// "Swap-AB" tiling: the UMMA M dimension (128 TMEM lanes) runs over output features, the UMMA N
+// dimension (128 TMEM columns) over tokens, so a CTA owns Y[tok0:tok0+128, f0:f0+128]^T:
+//   * A operand (weights): each thread dequantises one Q4 block per 64-wide K chunk into two bf16
+//     K-major tiles in shared memory (no-swizzle "interleaved" UMMA layout: 8x16-byte core matrices);
+//   * B operand (tokens): the activation producer (split_tiles_kernel) already wrote x_h/x_m/x_l as
+//     bf16 tiles in exactly that shared-memory layout, so one 16 KB 1-D TMA bulk copy per piece and
+//     chunk fetches them -- no tensor maps;
+//   * one thread issues the tcgen05.mma's; tcgen05.commit -> mbarrier frees the stage (2 stages);
+//   * epilogue: tcgen05.ld 32 lanes x 32 columns per warp; lane = feature, so every column is a
+//     coalesced 128-byte store of Y[token][f0+32q .. +31]; bias / residual / GELU / SiLU*up fused.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.h"
+#include "kernels.h"
+
+namespace vox {
+
+void tc_count_launch(const char *name);
+
+namespace {
+
+constexpr int G5_THREADS = 256;
+constexpr int G5_BM = 128;   // features per CTA (UMMA M)
+constexpr int G5_BN = 128;   // tokens per CTA (UMMA N)
+constexpr int G5_BK = 64;    // K per pipeline stage
+constexpr int G5_TILE_BYTES = G5_BM * G5_BK * 2;          // 16 KB: one bf16 operand tile
+constexpr int G5_STAGE_BYTES = 5 * G5_TILE_BYTES;         // w_hi, w_lo, x_h, x_m, x_l
+constexpr int G5_STAGES = 2;
+constexpr int G5_TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "G5_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra G5_DONE;\n"
+        "bra G5_WAIT;\n"
+        "G5_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes stored as 128
+// contiguous bytes; LBO = byte distance between the two 8-element K chunks of one MMA, SBO = byte
+// distance between consecutive 8-row groups; bits [46,48) = 1 (descriptor version for sm_100).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor for kind::f16: D = f32, A = B = bf16, both K-major, M x N tile
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct G5Args {
+    const uint4 *qs;      // row-major Q4 planes (kernels.h Q4Weight)
+    const __half *ds;
+    int N, K, M;          // M = tokens
+    const __nv_bfloat16 *xt;  // [3][TT][KC][8][128][8] tiled splits of X (zero padded rows)
+    int TT, KC;
+    float *y;
+    int ldy;
+    const float *bias, *res;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[G5_STAGES], done_bar[G5_STAGES];
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int f0 = blockIdx.x * G5_BM, tt = blockIdx.y, tok0 = tt * G5_BN;
+    const int bpr = a.K >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < G5_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&done_bar[s], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(G5_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+    const uint32_t idesc = umma_idesc_bf16(G5_BM, G5_BN);
+
+    // dequant mapping: thread -> (feature row, block within the 64-wide chunk)
+    const int drow = tid >> 1, dblk = tid & 1;
+    const int gn = f0 + drow;
+    const size_t xt_piece = (size_t)a.TT * a.KC * (G5_TILE_BYTES / 2);  // elements per split piece
+
+    for (int kc = 0; kc < a.KC; ++kc) {
+        const int s = kc & 1, use = kc >> 1;
+        unsigned char *stage = smem + (size_t)s * G5_STAGE_BYTES;
+        if (kc >= G5_STAGES) {
+            mbar_wait(&done_bar[s], (uint32_t)((use - 1) & 1));  // MMAs that read this stage have retired
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        }
+        if (tid == 0) {
+            mbar_expect_tx(&full_bar[s], 3 * G5_TILE_BYTES);
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                const __nv_bfloat16 *src = a.xt + p * xt_piece + ((size_t)tt * a.KC + kc) * (G5_TILE_BYTES / 2);
+                bulk_g2s(stage + (2 + p) * G5_TILE_BYTES, src, G5_TILE_BYTES, &full_bar[s]);
+            }
+        }
+        // ---- dequantise one Q4 block (32 weights) of row `gn` into the w_hi / w_lo tiles
+        {
+            uint4 q = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
+            float dd = 0.0f;
+            if (gn < a.N) {
+                const size_t blk = (size_t)gn * bpr + (size_t)kc * 2 + dblk;
+                q = __ldg(a.qs + blk);
+                dd = __half2float(__ldg(a.ds + blk));
+            }
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+            float wl[16], wh[16];  // elements 0..15 (low nibbles), 16..31 (high nibbles)
+#pragma unroll
+            for (int wi = 0; wi < 4; ++wi)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t byte = (w4[wi] >> (8 * t)) & 0xFFu;
+                    wl[wi * 4 + t] = ((float)(byte & 0xFu) - 8.0f) * dd;
+                    wh[wi * 4 + t] = ((float)(byte >> 4) - 8.0f) * dd;
+                }
+            // tile layout: [8 k-chunks of 8 elements][128 rows][16 bytes]
+            unsigned char *thi = stage, *tlo = stage + G5_TILE_BYTES;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {  // this block covers k-chunks dblk*4 + c
+                const float *src = (c < 2) ? (wl + c * 8) : (wh + (c - 2) * 8);
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float v0 = src[2 * e], v1 = src[2 * e + 1];
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                    const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+                    const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+                    ph[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    pl[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                const int off = (dblk * 4 + c) * (G5_BM * 16) + drow * 16;
+                *reinterpret_cast<uint4 *>(thi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<uint4 *>(tlo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes -> async (UMMA) reads
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(&full_bar[s], (uint32_t)(use & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t base = smem_u32(stage);
+            const uint32_t lbo = G5_BM * 16, sbo = 128;  // K-chunk stride, 8-row group stride
+#pragma unroll
+            for (int ks = 0; ks < G5_BK / 16; ++ks) {
+                const uint32_t koff = (uint32_t)ks * 2u * lbo;
+                const uint64_t whi = umma_desc(base + 0 * G5_TILE_BYTES + koff, lbo, sbo);
+                const uint64_t wlo = umma_desc(base + 1 * G5_TILE_BYTES + koff, lbo, sbo);
+                const uint64_t xh = umma_desc(base + 2 * G5_TILE_BYTES + koff, lbo, sbo);
+                const uint64_t xm = umma_desc(base + 3 * G5_TILE_BYTES + koff, lbo, sbo);
+                const uint64_t xl = umma_desc(base + 4 * G5_TILE_BYTES + koff, lbo, sbo);
+                // smallest terms first
+                umma_bf16(tmem_d, wlo, xm, idesc, (kc | ks) != 0);
+                umma_bf16(tmem_d, whi, xl, idesc, 1);
+                umma_bf16(tmem_d, wlo, xh, idesc, 1);
+                umma_bf16(tmem_d, whi, xm, idesc, 1);
+                umma_bf16(tmem_d, whi, xh, idesc, 1);
+            }
+            umma_commit(&done_bar[s]);
+        }
+    }
+    // ---- wait for the last commit of each stage (covers every MMA issued before it)
+    {
+        const int last = a.KC - 1;
+        for (int s = 0; s < G5_STAGES; ++s) {
+            const int kc_s = ((last & 1) == s) ? last : last - 1;
+            if (kc_s >= 0) mbar_wait(&done_bar[s], (uint32_t)((kc_s >> 1) & 1));
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    }
+    // ---- epilogue: warp w reads TMEM lanes 32*(w%4).. (features), columns 64*(w/4).. (tokens)
+    {
+        const int q4 = warp & 3, hcol = warp >> 2;
+        const int feat = f0 + q4 * 32 + lane;
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+            const int col0 = hcol * 64 + cb * 32;
+            uint32_t r[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            const float bsv = (a.bias && feat < a.N) ? a.bias[feat] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int tok = tok0 + col0 + j;
+                float v = __uint_as_float(r[j]);
+                if (EPI == EPI_SILU_MUL) {
+                    // features (2i, 2i+1) = (gate, up) sit in adjacent lanes
+                    const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+                    if ((lane & 1) == 0 && tok < a.M && feat + 1 < a.N)
+                        a.y[(size_t)tok * a.ldy + (feat >> 1)] = (v / (1.0f + expf(-v))) * other;
+                } else if (tok < a.M && feat < a.N) {
+                    v += bsv;
+                    if (EPI == EPI_RESIDUAL) v += a.res[(size_t)tok * a.ldy + feat];
+                    if (EPI == EPI_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+                    a.y[(size_t)tok * a.ldy + feat] = v;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(G5_TMEM_COLS) : "memory");
+    }
+}
+
+// X (f32, row-major [M][K]) -> three bf16 pieces in the UMMA tile layout, optionally through RMSNorm
+// (x / sqrt(mean(x^2)+eps) * gamma (* ada)).  CTA = 8 token rows; rows >= M are written as zeros.
+__global__ void __launch_bounds__(256) split_tiles_kernel(const float *__restrict__ x, int M, int K, const float *__restrict__ gamma,
+                                                          const float *__restrict__ ada, float eps,
+                                                          __nv_bfloat16 *__restrict__ xt, int TT, int KC) {
+    __shared__ float ssq_part[32][8];
+    __shared__ float rms_s[8];
+    const int r8 = threadIdx.x & 7, cth = threadIdx.x >> 3;  // cth: 0..31 strides over the 16-byte chunks
+    const int row = blockIdx.x * 8 + r8;
+    const int nchunk = K >> 3;
+    const bool valid = row < M;
+    const float *xr = x + (size_t)(valid ? row : 0) * K;
+    if (gamma) {
+        float ssq = 0.0f;
+        if (valid)
+            for (int c = cth; c < nchunk; c += 32) {
+                const float4 v0 = *reinterpret_cast<const float4 *>(xr + c * 8);
+                const float4 v1 = *reinterpret_cast<const float4 *>(xr + c * 8 + 4);
+                ssq = fmaf(v0.x, v0.x, ssq); ssq = fmaf(v0.y, v0.y, ssq); ssq = fmaf(v0.z, v0.z, ssq); ssq = fmaf(v0.w, v0.w, ssq);
+                ssq = fmaf(v1.x, v1.x, ssq); ssq = fmaf(v1.y, v1.y, ssq); ssq = fmaf(v1.z, v1.z, ssq); ssq = fmaf(v1.w, v1.w, ssq);
+            }
+        ssq_part[cth][r8] = ssq;
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            float s = 0.0f;
+            for (int i = 0; i < 32; ++i) s += ssq_part[i][threadIdx.x];
+            rms_s[threadIdx.x] = sqrtf(s / (float)K + eps);
+        }
+        __syncthreads();
+    }
+    const float rms = gamma ? rms_s[r8] : 1.0f;
+    const int tt = row / G5_BN, rin = row % G5_BN;
+    const size_t piece = (size_t)TT * KC * (G5_TILE_BYTES / 2);
+    for (int c = cth; c < nchunk; c += 32) {
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (valid) {
+            const float4 v0 = *reinterpret_cast<const float4 *>(xr + c * 8);
+            const float4 v1 = *reinterpret_cast<const float4 *>(xr + c * 8 + 4);
+            v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+            if (gamma) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    v[e] = (v[e] / rms) * gamma[c * 8 + e];
+                    if (ada) v[e] *= ada[c * 8 + e];
+                }
+            }
+        }
+        uint32_t p[3][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            uint32_t w[3] = {0, 0, 0};
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const float f = v[2 * e + hlf];
+                const __nv_bfloat16 bh = __float2bfloat16_rn(f);
+                const float r1 = f - __bfloat162float(bh);
+                const __nv_bfloat16 bm = __float2bfloat16_rn(r1);
+                const float r2 = r1 - __bfloat162float(bm);
+                const __nv_bfloat16 bl = __float2bfloat16_rn(r2);
+                w[0] |= (uint32_t)__bfloat16_as_ushort(bh) << (16 * hlf);
+                w[1] |= (uint32_t)__bfloat16_as_ushort(bm) << (16 * hlf);
+                w[2] |= (uint32_t)__bfloat16_as_ushort(bl) << (16 * hlf);
+            }
+            p[0][e] = w[0]; p[1][e] = w[1]; p[2][e] = w[2];
+        }
+        // tile (tt, kc = c/8), chunk-in-tile c%8, row rin: [8][128][16 B]
+        const size_t off = ((size_t)tt * KC + (c >> 3)) * (G5_TILE_BYTES / 2) + (size_t)((c & 7) * G5_BN + rin) * 8;
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+            *reinterpret_cast<uint4 *>(xt + s * piece + off) = make_uint4(p[s][0], p[s][1], p[s][2], p[s][3]);
+    }
+}
+
+}  // namespace
+
+bool gemm_tc5_supported(const Q4Weight &w, int M) { return w.N % G5_BM == 0 && w.K % G5_BK == 0 && M >= 1; }
+
+size_t gemm_tc5_split_elems(int M, int K) {
+    const size_t TT = (size_t)(M + G5_BN - 1) / G5_BN;
+    return 3 * TT * (size_t)(K / G5_BK) * (G5_TILE_BYTES / 2);
+}
+
+// x [M][K] f32 -> xt (bf16 pieces, tile layout); rows padded to a multiple of 128 with zeros
+void launch_split_tiles(const float *x, int M, int K, const float *gamma, const float *ada, float eps, void *xt,
+                        cudaStream_t st) {
+    VOX_CHECK(K % G5_BK == 0, VOX_EINVAL, "split_tiles: K=%d not a multiple of 64", K);
+    const int TT = (M + G5_BN - 1) / G5_BN, KC = K / G5_BK;
+    split_tiles_kernel<<<TT * (G5_BN / 8), 256, 0, st>>>(x, M, K, gamma, ada, eps, (__nv_bfloat16 *)xt, TT, KC);
+    tc_count_launch("split_tiles");
+}
+
+void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int ldy, const float *bias, const float *res,
+                        int epi, cudaStream_t st) {
+    VOX_CHECK(gemm_tc5_supported(w, M), VOX_EINVAL, "gemm_tc5: unsupported shape N=%d K=%d", w.N, w.K);
+    G5Args a{};
+    a.qs = w.qs;
+    a.ds = w.d;
+    a.N = w.N;
+    a.K = w.K;
+    a.M = M;
+    a.xt = (const __nv_bfloat16 *)xt;
+    a.TT = (M + G5_BN - 1) / G5_BN;
+    a.KC = w.K / G5_BK;
+    a.y = y;
+    a.ldy = ldy;
+    a.bias = bias;
+    a.res = res;
+    const size_t smem = (size_t)G5_STAGES * G5_STAGE_BYTES + 1024;
+    dim3 grid(w.N / G5_BM, a.TT);
+#define G5_CASE(E)                                                                                              \
+    case E: {                                                                                                   \
+        static bool set = false;                                                                                \
+        if (!set) {                                                                                             \
+            cudaFuncSetAttribute(gemm_tc5_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+            set = true;                                                                                         \
+        }                                                                                                       \
+        gemm_tc5_kernel<E><<<grid, G5_THREADS, smem, st>>>(a);                                                  \
+        break;                                                                                                  \
+    }
+    switch (epi) {
+        G5_CASE(EPI_NONE)
+        G5_CASE(EPI_RESIDUAL)
+        G5_CASE(EPI_SILU_MUL)
+        G5_CASE(EPI_GELU)
+        default: fail(VOX_EINVAL, "bad epilogue");
+    }
+#undef G5_CASE
+    tc_count_launch("gemm_tc5");
+}
+
+}  // namespace vox

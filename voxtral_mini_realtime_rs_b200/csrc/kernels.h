@@ -62,6 +62,14 @@ void launch_dec_attn_fused(float *qkv, int B, int ld, int H, int Hkv, int hd, fl
 // y[M,N] = A[M,K] . W^T for any M (encoder / prefill): tiled SIMT GEMM, in-tile dequant.
 void launch_q4_gemm(const Q4Weight &w, const float *a, int M, float *y, int ldy, const float *bias,
                     const float *res, int epi, cudaStream_t st);
+// tcgen05 path (gemm_tc5.cu): X is first split into three bf16 pieces laid out as UMMA operand tiles
+// (optionally through RMSNorm), then Y = X . W^T with f32-grade accuracy on the tensor cores.
+bool gemm_tc5_supported(const Q4Weight &w, int M);
+size_t gemm_tc5_split_elems(int M, int K);  // bf16 elements needed for the split buffer
+void launch_split_tiles(const float *x, int M, int K, const float *gamma, const float *ada, float eps, void *xt,
+                        cudaStream_t st);
+void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int ldy, const float *bias, const float *res,
+                        int epi, cudaStream_t st);
 // conv2 as implicit GEMM: in [B][T_in][C_in] time-major, W [C_out][3*C_in] (k = tap*C_in + c),
 // stride 2, pad 1, + bias, GELU -> out [B][T_out][C_out].
 void launch_conv2_gemm(const float *in, const float *w, const float *bias, float *out, int B, int T_in,

@@ -422,6 +422,17 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
         s->d_tok = s->arena.alloc_n<int>(B);
         s->d_ids = s->arena.alloc_n<int>(drows);
         s->d_out = s->arena.alloc_n<int>(B * s->out_ld);
+        {   // split-tile buffer of the tcgen05 GEMM: largest (rows, K) pair it is used with
+            const int rows_e = max_batch * s->S_max, rows_d = max_batch * s->M_max;
+            size_t e = 0;
+            for (int K : {c.enc_dim, c.enc_heads * c.enc_head_dim, c.enc_ffn}) e = std::max(e, gemm_tc5_split_elems(rows_e, K / 64 * 64));
+            e = std::max(e, gemm_tc5_split_elems(max_batch * std::max(s->S4_max, 1), c.enc_dim * c.reshape_factor / 64 * 64));
+            for (int K : {c.dec_dim, c.dec_heads * c.dec_head_dim, c.dec_ffn}) e = std::max(e, gemm_tc5_split_elems(std::max(rows_d, max_batch * std::max(s->S4_max, 1)), K / 64 * 64));
+            s->xt_elems = e;
+            s->xt_buf = s->arena.alloc(e * 2);
+            const char *gv = getenv("VOX_GEMM");
+            s->use_gemm_tc = !(gv && std::string(gv) == "simt");
+        }
         {   // fused-decode scratch (see TcWork): sized for the largest split-K matvec at max_batch rows
             const int mb = std::min(8, max_batch * 1);
             size_t need = 0;
@@ -465,8 +476,27 @@ Session::~Session() {
     if (st) cudaStreamDestroy(st);
 }
 
+void Session::linear_n(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias, const float *res,
+                       int epi, const float *gamma, const float *ada, float *tmp) {
+    if (M > 8 && use_gemm_tc && gemm_tc5_supported(w, M) && gemm_tc5_split_elems(M, w.K) <= xt_elems) {
+        launch_split_tiles(x, M, w.K, gamma, ada, m->norm_eps, xt_buf, st);
+        launch_q4_gemm_tc5(w, xt_buf, M, y, ldy, bias, res, epi, st);
+        return;
+    }
+    if (gamma) {
+        launch_rmsnorm(x, gamma, ada, tmp, M, w.K, m->norm_eps, st);
+        x = tmp;
+    }
+    linear(w, x, M, y, ldy, bias, res, epi);
+}
+
 void Session::linear(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias,
                      const float *res, int epi) {
+    if (M > 8 && use_gemm_tc && gemm_tc5_supported(w, M) && gemm_tc5_split_elems(M, w.K) <= xt_elems) {
+        launch_split_tiles(x, M, w.K, nullptr, nullptr, 0.0f, xt_buf, st);
+        launch_q4_gemm_tc5(w, xt_buf, M, y, ldy, bias, res, epi, st);
+        return;
+    }
     if (M <= 8 && w.qs_tc && use_tc) launch_q4_matvec_tc(w, x, M, y, ldy, bias, res, epi, st);
     else if (M <= 8) launch_q4_matvec(w, x, M, y, ldy, bias, res, epi, st);
     else launch_q4_gemm(w, x, M, y, ldy, bias, res, epi, st);
@@ -507,15 +537,13 @@ void Session::encode(int B, int T) {
     const float scale = powf((float)c.enc_head_dim, -0.5f);
     for (int i = 0; i < c.enc_layers; ++i) {
         const EncLayerW &l = m->enc[i];
-        launch_rmsnorm(x_enc, l.attn_norm, nullptr, h_enc, rows, d, m->norm_eps, st);
-        linear(l.wqkv, h_enc, rows, qkv_enc, 3 * hdq, l.bqkv, nullptr, EPI_NONE);
+        linear_n(l.wqkv, x_enc, rows, qkv_enc, 3 * hdq, l.bqkv, nullptr, EPI_NONE, l.attn_norm, nullptr, h_enc);
         launch_rope_inplace(qkv_enc, rows, 3 * hdq, 0, c.enc_heads, hdq, c.enc_heads, c.enc_head_dim, S, 0,
                             m->enc_cos, m->enc_sin, st);
         launch_enc_attention(qkv_enc, attn_enc, B, S, c.enc_heads, c.enc_head_dim, 3 * hdq, 0, hdq, 2 * hdq,
                              c.enc_window, scale, st);
         linear(l.wo, attn_enc, rows, x_enc, d, l.bo, x_enc, EPI_RESIDUAL);
-        launch_rmsnorm(x_enc, l.ffn_norm, nullptr, h_enc, rows, d, m->norm_eps, st);
-        linear(l.w13, h_enc, rows, act_enc, c.enc_ffn, nullptr, nullptr, EPI_SILU_MUL);
+        linear_n(l.w13, x_enc, rows, act_enc, c.enc_ffn, nullptr, nullptr, EPI_SILU_MUL, l.ffn_norm, nullptr, h_enc);
         linear(l.w2, act_enc, rows, x_enc, d, l.b2, x_enc, EPI_RESIDUAL);
         if (debug_capture && dbg_layers)
             CUDA_OK(cudaMemcpyAsync(dbg_layers + (size_t)i * rows * d, x_enc, sizeof(float) * rows * d,
@@ -569,8 +597,7 @@ bool Session::decoder_forward(int B, int M) {
             launch_q4_matvec_tc_ex(l.wqkv, x_dec, rows, qkv_dec, qkvd, nullptr, nullptr, EPI_NONE, l.attn_norm, nullptr,
                                    m->norm_eps, &wk_norm, st);
         } else {
-            launch_rmsnorm(x_dec, l.attn_norm, nullptr, h_dec, rows, D, m->norm_eps, st);
-            linear(l.wqkv, h_dec, rows, qkv_dec, qkvd, nullptr, nullptr, EPI_NONE);
+            linear_n(l.wqkv, x_dec, rows, qkv_dec, qkvd, nullptr, nullptr, EPI_NONE, l.attn_norm, nullptr, h_dec);
         }
         if (fattn) {
             launch_dec_attn_fused(qkv_dec, B, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, c.dec_window, scale, m->dec_cos,
@@ -587,8 +614,7 @@ bool Session::decoder_forward(int B, int M) {
             launch_q4_matvec_tc_ex(l.w13, x_dec, rows, act_dec, c.dec_ffn, nullptr, nullptr, EPI_SILU_MUL, l.ffn_norm,
                                    ada + (size_t)j * D, m->norm_eps, &wk_norm, st);
         } else {
-            launch_rmsnorm(x_dec, l.ffn_norm, ada + (size_t)j * D, h_dec, rows, D, m->norm_eps, st);
-            linear(l.w13, h_dec, rows, act_dec, c.dec_ffn, nullptr, nullptr, EPI_SILU_MUL);
+            linear_n(l.w13, x_dec, rows, act_dec, c.dec_ffn, nullptr, nullptr, EPI_SILU_MUL, l.ffn_norm, ada + (size_t)j * D, h_dec);
         }
         if (fused)
             launch_q4_matvec_tc_ex(l.w2, act_dec, rows, x_dec, D, nullptr, x_dec, EPI_RESIDUAL, nullptr, nullptr, 0.f, &wk_res, st);

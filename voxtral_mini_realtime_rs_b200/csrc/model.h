@@ -119,6 +119,13 @@ struct Session {
     int *am_idx = nullptr, *am_cnt = nullptr;
     TcWork tc_work(bool norm_in, bool ssq_out) const;
     bool fused_decode(int rows) const;
+    void *xt_buf = nullptr;   // bf16 split tiles feeding the tcgen05 GEMM
+    size_t xt_elems = 0;
+    bool use_gemm_tc = true;  // tcgen05 GEMM for M > 8 (VOX_GEMM=simt disables)
+    // y = epi(norm(x) . W^T): RMSNorm fused into the operand split when the tcgen05 path applies,
+    // else rmsnorm into `tmp` + linear()
+    void linear_n(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias, const float *res, int epi,
+                  const float *gamma, const float *ada, float *tmp);
     bool use_tc = true;  // tensor-core-assisted matvec for M <= 8 (VOX_MATVEC=simt disables)
     std::vector<float> enc_debug;  // per-layer captures when debugging is enabled
     bool debug_capture = false;
