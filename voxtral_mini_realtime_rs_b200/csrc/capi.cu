@@ -512,6 +512,7 @@ static void upload_mel(Session *s, const float *mel, int b, int t) {
               s->max_mel_frames);
     CUDA_OK(cudaSetDevice(s->m->device));
     CUDA_OK(cudaMemcpyAsync(s->mel, mel, sizeof(float) * (size_t)b * c.n_mels * t, cudaMemcpyHostToDevice, s->st));
+    launch_transpose_mel(s->mel, s->mel_tm, b, c.n_mels, t, s->st);
 }
 
 int32_t vox_encode_audio(vox_session *sh, const float *mel, int32_t b, int32_t t, float *audio_embeds, size_t cap,
@@ -588,7 +589,7 @@ static int32_t transcribe_pcm_impl(Session *s, const float *host, const float *d
     }
     launch_peak_normalize_pad(src, b, n, 0.95f, normalize, s->pcm_pad, padded, left, s->peak_scale, s->st);
     launch_mel(s->pcm_pad, b, padded, padded, s->m->mel.window, s->m->mel.fb_vals, s->m->mel.fb_start, s->m->mel.fb_len,
-               s->m->mel.fb_stride, s->mel, (int)frames, 1, s->st);
+               s->m->mel.fb_stride, s->mel_tm, (int)frames, 0, s->st);
     CUDA_OK(cudaEventRecord(s->ev[1], s->st));
     (void)c;
     *n_out = s->transcribe_from_mel(b, (int)frames, out_ids, cap, tm, true);

@@ -432,6 +432,25 @@ __global__ void conv1_kernel(const float *__restrict__ mel, const float *__restr
     }
 }
 
+__global__ void transpose_mel_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int T) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, t = t0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && t < T) ? in[((size_t)b * C + c) * T + t] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int t = t0 + i, c = c0 + threadIdx.x;
+        if (t < T && c < C) out[((size_t)b * T + t) * C + c] = tile[threadIdx.x][i];
+    }
+}
+void launch_transpose_mel(const float *in, float *out, int B, int C, int T, cudaStream_t st) {
+    dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    transpose_mel_kernel<<<grid, block, 0, st>>>(in, out, C, T);
+    post_launch("transpose_mel");
+}
+
 void launch_conv1(const float *mel, const float *w, const float *bias, float *out, int B, int C_in, int T,
                   int T_out, int C_out, cudaStream_t st) {
     dim3 grid(T_out, B);
@@ -516,10 +535,10 @@ __global__ void __launch_bounds__(EA_THREADS)
 enc_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out, int S, int H, int ld, int q_off,
                      int k_off, int v_off, int window, float scale) {
     extern __shared__ __align__(16) float sm[];
-    float *Qs = sm;                          // [32][HD]
-    float *Ks = Qs + EA_BQ * HD;             // [64][HD+1]
+    float *Qs = sm;                          // [32][HD+1]  (odd strides: rows map to distinct banks)
+    float *Ks = Qs + EA_BQ * (HD + 1);       // [64][HD+1]
     float *Vs = Ks + EA_BK * (HD + 1);       // [64][HD]
-    float *Ps = Vs + EA_BK * HD;             // [32][64]
+    float *Ps = Vs + EA_BK * HD;             // [32][65]
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * EA_BQ;
     const int tid = threadIdx.x, r = tid >> 2, c = tid & 3;
     constexpr int DQ = HD / 4;
@@ -527,7 +546,7 @@ enc_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out, int
     for (int i = tid; i < EA_BQ * HD; i += EA_THREADS) {
         const int rr = i / HD, d = i - rr * HD;
         const int gi = q0 + rr;
-        Qs[i] = gi < S ? base[(size_t)gi * ld + q_off + h * HD + d] : 0.0f;
+        Qs[rr * (HD + 1) + d] = gi < S ? base[(size_t)gi * ld + q_off + h * HD + d] : 0.0f;
     }
     const int gi = q0 + r;
     float o[DQ];
@@ -558,7 +577,7 @@ enc_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out, int
         for (int jj = 0; jj < 16; ++jj) {
             const int kk = c + 4 * jj;
             const int gj = j0 + kk;
-            const float *qr = Qs + r * HD;
+            const float *qr = Qs + r * (HD + 1);
             const float *kr = Ks + kk * (HD + 1);
             float acc = 0.0f;
 #pragma unroll 16
@@ -573,14 +592,14 @@ enc_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out, int
         float alpha = 1.0f, psum = 0.0f;
         if (m_new == -INFINITY) {
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) Ps[r * EA_BK + c + 4 * jj] = 0.0f;
+            for (int jj = 0; jj < 16; ++jj) Ps[r * (EA_BK + 1) + c + 4 * jj] = 0.0f;
         } else {
             alpha = expf(m_run - m_new);
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
                 const float pv = expf(s[jj] - m_new);
                 psum += pv;
-                Ps[r * EA_BK + c + 4 * jj] = pv;
+                Ps[r * (EA_BK + 1) + c + 4 * jj] = pv;
             }
         }
         psum += __shfl_xor_sync(0xffffffffu, psum, 1);
@@ -591,17 +610,17 @@ enc_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out, int
         for (int d = 0; d < DQ; ++d) o[d] *= alpha;
         __syncwarp();
         for (int kk = 0; kk < EA_BK; ++kk) {
-            const float pv = Ps[r * EA_BK + kk];
-            const float *vr = Vs + kk * HD + c * DQ;
+            const float pv = Ps[r * (EA_BK + 1) + kk];
+            const float *vr = Vs + kk * HD + c;  // thread c owns head dims d = 4 i + c: conflict-free V reads
 #pragma unroll
-            for (int d = 0; d < DQ; ++d) o[d] = fmaf(pv, vr[d], o[d]);
+            for (int d = 0; d < DQ; ++d) o[d] = fmaf(pv, vr[4 * d], o[d]);
         }
     }
     if (gi < S) {
         const float inv = 1.0f / l_run;
-        float *orow = out + ((size_t)b * S + gi) * (H * HD) + h * HD + c * DQ;
+        float *orow = out + ((size_t)b * S + gi) * (H * HD) + h * HD + c;
 #pragma unroll
-        for (int d = 0; d < DQ; ++d) orow[d] = o[d] * inv;
+        for (int d = 0; d < DQ; ++d) orow[4 * d] = o[d] * inv;
     }
 }
 
@@ -609,7 +628,7 @@ void launch_enc_attention(const float *qkv, float *out, int B, int S, int H, int
                           int k_off, int v_off, int window, float scale, cudaStream_t st) {
     if (S <= 0) return;
     dim3 grid((S + EA_BQ - 1) / EA_BQ, H, B);
-    const size_t smem = (size_t)(EA_BQ * hd + EA_BK * (hd + 1) + EA_BK * hd + EA_BQ * EA_BK) * sizeof(float);
+    const size_t smem = (size_t)(EA_BQ * (hd + 1) + EA_BK * (hd + 1) + EA_BK * hd + EA_BQ * (EA_BK + 1)) * sizeof(float);
 #define ENC_ATTN_CASE(HD)                                                                                   \
     case HD: {                                                                                              \
         static bool set = false;                                                                            \

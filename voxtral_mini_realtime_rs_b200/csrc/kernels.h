@@ -74,6 +74,8 @@ void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int 
 // stride 2, pad 1, + bias, GELU -> out [B][T_out][C_out].
 void launch_conv2_gemm(const float *in, const float *w, const float *bias, float *out, int B, int T_in,
                        int T_out, int C_in, int C_out, cudaStream_t st);
+// [B][C][T] -> [B][T][C]
+void launch_transpose_mel(const float *in, float *out, int B, int C, int T, cudaStream_t st);
 // conv1: mel [B][C_in][T] channel-major, W [C_out][C_in][3] -> GELU -> out [B][T_out][C_out].
 void launch_conv1(const float *mel, const float *w, const float *bias, float *out, int B, int C_in, int T,
                   int T_out, int C_out, cudaStream_t st);

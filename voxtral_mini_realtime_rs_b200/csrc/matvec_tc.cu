@@ -453,6 +453,12 @@ void tc_launch_t(TcArgs a, const TcWork *wk, cudaStream_t st) {
     const size_t slice_bytes = (size_t)Ps * 576;
     int TG = (int)((20 * 1024 + slice_bytes - 1) / slice_bytes);
     TG = TG < 1 ? 1 : (TG > 4 ? 4 : TG);
+    // the activation staging is per CTA: with several tokens it is a sizeable share of the work, so
+    // give each CTA enough tiles to amortise it while keeping ~4 CTAs per SM in flight
+    if (M > 2) {
+        const int tg_occ = (int)(((size_t)a.n_tiles * S + 148 * 4 - 1) / (148 * 4));
+        if (tg_occ > TG) TG = tg_occ > 16 ? 16 : tg_occ;
+    }
     while (TG > 1 && (size_t)((a.n_tiles + TG - 1) / TG) * S < 2 * 148) --TG;
     const int nbuf = TG > 1 ? 2 : 1;
     const size_t misc = (12 + TC_WARPS * M + TC_WARPS * 16 * M + 2 * 16 * M) * sizeof(float);

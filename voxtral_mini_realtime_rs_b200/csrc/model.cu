@@ -282,7 +282,16 @@ Model *Model::load(const Gguf &g, int device) {
 
         const int d = c.enc_dim, hdq = c.enc_heads * c.enc_head_dim, D = c.dec_dim;
         // ---- conv downsampler (loader.rs:263-275), f32 ----
-        m.conv1_w = L.f32_dev(E + ".conv_layers.0.conv.weight", {d, c.n_mels, 3});
+        {   // conv1 weights [o][c][tap] -> [o][tap*n_mels + c]: conv1 runs as an implicit GEMM on the
+            // time-major mel like conv2
+            std::vector<float> w = L.f32(E + ".conv_layers.0.conv.weight", {d, c.n_mels, 3});
+            std::vector<float> r((size_t)d * 3 * c.n_mels);
+            for (int o = 0; o < d; ++o)
+                for (int ci = 0; ci < c.n_mels; ++ci)
+                    for (int t = 0; t < 3; ++t)
+                        r[(size_t)o * 3 * c.n_mels + (size_t)t * c.n_mels + ci] = w[((size_t)o * c.n_mels + ci) * 3 + t];
+            m.conv1_w = m.arena.upload(r.data(), r.size());
+        }
         m.conv1_b = L.f32_dev(E + ".conv_layers.0.conv.bias", {d});
         {
             std::vector<float> w = L.f32(E + ".conv_layers.1.conv.weight", {d, d, 3});
@@ -387,6 +396,7 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
         const size_t B = max_batch;
         const int hdq = c.enc_heads * c.enc_head_dim;
         s->mel = s->arena.alloc_n<float>(B * c.n_mels * max_mel_frames);
+        s->mel_tm = s->arena.alloc_n<float>(B * c.n_mels * max_mel_frames);
         s->peak_scale = s->arena.alloc_n<float>(B);
         s->h1 = s->arena.alloc_n<float>(B * s->T1_max * c.enc_dim);
         const size_t rows = B * s->S_max;
@@ -531,7 +541,8 @@ void Session::encode(int B, int T) {
     const int T1 = conv_out(T), S = conv_out(T1), S4 = S / c.reshape_factor;
     const int d = c.enc_dim, hdq = c.enc_heads * c.enc_head_dim;
     const int rows = B * S;
-    launch_conv1(mel, m->conv1_w, m->conv1_b, h1, B, c.n_mels, T, T1, d, st);
+    // conv1 + GELU as implicit GEMM over the time-major mel [B][T][128] (K = 3*128)
+    launch_conv2_gemm(mel_tm, m->conv1_w, m->conv1_b, h1, B, T, T1, c.n_mels, d, st);
     launch_conv2_gemm(h1, m->conv2_w, m->conv2_b, x_enc, B, T1, S, d, d, st);
     if (debug_capture && dbg_conv) CUDA_OK(cudaMemcpyAsync(dbg_conv, x_enc, sizeof(float) * rows * d, cudaMemcpyDeviceToDevice, st));
     const float scale = powf((float)c.enc_head_dim, -0.5f);

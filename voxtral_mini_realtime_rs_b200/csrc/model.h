@@ -88,7 +88,8 @@ struct Session {
     // audio
     float *pcm = nullptr, *pcm_pad = nullptr, *peak_scale = nullptr;
     size_t pcm_cap = 0, pcm_pad_cap = 0;
-    float *mel = nullptr;
+    float *mel = nullptr;     // [B][128][T] as handed in by callers (reference layout)
+    float *mel_tm = nullptr;  // [B][T][128] time-major copy consumed by the conv1 implicit GEMM
     // encoder workspace
     float *h1 = nullptr, *x_enc = nullptr, *h_enc = nullptr, *qkv_enc = nullptr, *attn_enc = nullptr, *act_enc = nullptr;
     float *packed = nullptr, *adapter_h = nullptr, *audio = nullptr;
@@ -135,7 +136,7 @@ struct Session {
     static Session *create(Model *m, int max_batch, int max_mel_frames);
     ~Session();
     void set_delay(float delay);
-    // mel [B][128][T] already on device in s->mel
+    // mel already on device, time-major, in s->mel_tm
     void encode(int B, int T);
     void linear(const Q4Weight &w, const float *x, int M, float *y, int ldy, const float *bias, const float *res,
                 int epi);
