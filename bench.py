@@ -26,6 +26,12 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# the CPU legs interleave torch-CPU ops with an OpenMP C kernel: spinning worker pools of two
+# runtimes would fight over the cores, so make idle OpenMP threads sleep (must be set before import)
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+os.environ.setdefault("GOMP_SPINCOUNT", "0")
+os.environ.setdefault("KMP_BLOCKTIME", "0")
 import statistics
 import subprocess
 import sys
@@ -161,7 +167,7 @@ def cpu_port_decode_sample(n_tokens: int, threads: int):
     import torch
     from oracle import mel as omel
     from oracle.model import OracleModel
-    torch.set_num_threads(threads)
+    torch.set_num_threads(1)   # the torch ops at M=1 are tiny; the Q4 matvec (C, OpenMP) gets the cores
     om = OracleModel(GGUF_PATH, threads=threads)
     cfg = om.cfg
     ada = om.ada_scales(omel.time_embedding(6.0, cfg.dec_dim))
@@ -178,11 +184,16 @@ def cpu_port_decode_sample(n_tokens: int, threads: int):
     return n_tokens / dt, dt
 
 
+def cpu_threads() -> int:
+    """Threads for the CPU port: all cores up to 64 (the matvec is memory-bound beyond that)."""
+    return max(1, min(os.cpu_count() or 1, 64))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     ensure_gguf(0, lambda: None)
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     per_step = 2
     for _ in range(args.warmup):
         cpu_port_decode_sample(1, threads)
@@ -328,7 +339,7 @@ def run_ours(args, rank, local_rank, world):
     # CPU baseline (oracle port) on a bounded sample, N=1 only
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = cpu_threads()
         v, dt = cpu_port_decode_sample(args.cpu_tokens, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{args.cpu_tokens} single-token decode steps of 1 stream, full-size weights ({dt:.1f} s)"}
@@ -364,7 +375,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--streams", type=int, default=8, help="concurrent 16 s streams per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-tokens", type=int, default=4)
+    ap.add_argument("--cpu-tokens", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()

@@ -122,10 +122,12 @@ struct TcArgs {
 };
 
 // Effective activation value (after the optional fused RMSNorm).
-__device__ __forceinline__ float4 eff4(const float4 v, const float rms, const float *gamma, const float *ada, const int k) {
+// `rinv` = 1 / sqrt(mean(x^2)+eps): the reference divides (x / rms); multiplying by the reciprocal
+// differs by <= 1 ulp per element and removes ~10 instructions per element from the staging pass.
+__device__ __forceinline__ float4 eff4(const float4 v, const float rinv, const float *gamma, const float *ada, const int k) {
     if (!gamma) return v;
     const float4 g = *reinterpret_cast<const float4 *>(gamma + k);
-    float4 o = make_float4((v.x / rms) * g.x, (v.y / rms) * g.y, (v.z / rms) * g.z, (v.w / rms) * g.w);
+    float4 o = make_float4((v.x * rinv) * g.x, (v.y * rinv) * g.y, (v.z * rinv) * g.z, (v.w * rinv) * g.w);
     if (ada) {
         const float4 a = *reinterpret_cast<const float4 *>(ada + k);
         o.x *= a.x; o.y *= a.y; o.z *= a.z; o.w *= a.w;
@@ -253,7 +255,7 @@ template <int M, int EPI>
 __global__ void __launch_bounds__(TC_THREADS) q4_matvec_tc_kernel(const TcArgs a) {
     constexpr int CG = (M + 3) / 4;  // column groups of 8 (= 4 tokens x 2 splits)
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *rms = reinterpret_cast<float *>(smem_raw);                  // [8]
+    float *rms = reinterpret_cast<float *>(smem_raw);                  // [8] reciprocal rms per token
     int *flag = reinterpret_cast<int *>(rms + 8);                       // [1] (+3 pad)
     float *stat = rms + 12;                                             // [TC_WARPS][M] fallback ssq partials
     float *red = stat + TC_WARPS * M;                                   // [TC_WARPS][16 rows][M]
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS) q4_matvec_tc_kernel(const TcArgs a
                 for (int i = lane; i < a.ssq_in_parts; i += 32) s += a.ssq_in[(size_t)i * M + warp];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) rms[warp] = sqrtf(s / (float)a.K + a.eps);
+                if (lane == 0) rms[warp] = 1.0f / sqrtf(s / (float)a.K + a.eps);
             }
         } else {
             const int kq = a.K >> 2;
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS) q4_matvec_tc_kernel(const TcArgs a
                 float s = 0.0f;
 #pragma unroll
                 for (int w = 0; w < TC_WARPS; ++w) s += stat[w * M + threadIdx.x];
-                rms[threadIdx.x] = sqrtf(s / (float)a.K + a.eps);
+                rms[threadIdx.x] = 1.0f / sqrtf(s / (float)a.K + a.eps);
             }
         }
         __syncthreads();
@@ -400,19 +402,23 @@ __global__ void __launch_bounds__(TC_THREADS) q4_matvec_tc_kernel(const TcArgs a
             // deterministic split-K: publish partials, last CTA to arrive sums them in slice order
             for (int i = threadIdx.x; i < 16 * M; i += TC_THREADS) {
                 const int r = i / M, tok = i - r * M;
-                a.partial[((size_t)slice * M + tok) * a.ldp + tile * 16 + r] = vals[i];
+                __stcg(a.partial + ((size_t)slice * M + tok) * a.ldp + tile * 16 + r, vals[i]);
             }
-            __threadfence();
             __syncthreads();
             if (threadIdx.x == 0) {
+                // release: the barrier orders every thread's partial stores before this fence
+                // (fences are cumulative), so one gpu-scope fence per CTA is enough
+                __threadfence();
                 const int old = atomicAdd(&a.counters[tile], 1);
                 const int last = (old == a.S - 1);
-                if (last) a.counters[tile] = 0;  // all slices have arrived: reset for the next launch
+                if (last) {
+                    a.counters[tile] = 0;  // all slices have arrived: reset for the next launch
+                    __threadfence();       // acquire side: the other slices' partials are now visible in L2
+                }
                 *flag = last;
             }
             __syncthreads();
             if (*flag) {
-                __threadfence();
                 for (int i = threadIdx.x; i < 16 * M; i += TC_THREADS) {
                     const int r = i / M, tok = i - r * M;
                     float s = 0.0f;
