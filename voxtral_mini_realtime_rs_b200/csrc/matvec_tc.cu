@@ -447,7 +447,11 @@ bool g_tc_pdl = !(getenv("VOX_PDL") && getenv("VOX_PDL")[0] == '0');
 template <int M, int EPI>
 void tc_launch_t(TcArgs a, const TcWork *wk, cudaStream_t st) {
     // ---- work decomposition
-    const int ps_max = M <= 2 ? 64 : (M <= 4 ? 32 : 16);
+    // tuning knobs (environment, read once): VOX_TC_PS = K pairs per slice for M > 4,
+    // VOX_TC_CTAS = target resident CTAs per SM when several tokens share the staging
+    static const int env_ps = getenv("VOX_TC_PS") ? atoi(getenv("VOX_TC_PS")) : 0;
+    static const int env_ctas = getenv("VOX_TC_CTAS") ? atoi(getenv("VOX_TC_CTAS")) : 0;
+    const int ps_max = M <= 2 ? 64 : (M <= 4 ? 32 : (env_ps > 0 ? env_ps : 16));
     int S = 1;
     if (wk && wk->partial && wk->counters) S = (a.n_pairs + ps_max - 1) / ps_max;
     int Ps = (a.n_pairs + S - 1) / S;
@@ -462,7 +466,8 @@ void tc_launch_t(TcArgs a, const TcWork *wk, cudaStream_t st) {
     // the activation staging is per CTA: with several tokens it is a sizeable share of the work, so
     // give each CTA enough tiles to amortise it while keeping ~4 CTAs per SM in flight
     if (M > 2) {
-        const int tg_occ = (int)(((size_t)a.n_tiles * S + 148 * 4 - 1) / (148 * 4));
+        const int ctas = env_ctas > 0 ? env_ctas : 4;
+        const int tg_occ = (int)(((size_t)a.n_tiles * S + 148 * ctas - 1) / (148 * ctas));
         if (tg_occ > TG) TG = tg_occ > 16 ? 16 : tg_occ;
     }
     while (TG > 1 && (size_t)((a.n_tiles + TG - 1) / TG) * S < 2 * 148) --TG;
