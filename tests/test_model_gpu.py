@@ -20,6 +20,13 @@ def tiny_model(vx, tiny_gguf):
     m.close()
 
 
+@pytest.fixture(scope="module")
+def tiny_model8(vx, tiny_gguf):
+    m = vx.Q4ModelLoader.from_file(tiny_gguf).load(0, max_batch=8, max_mel_frames=1500)
+    yield m
+    m.close()
+
+
 def _mel(seconds, seed=1234):
     a = omel.peak_normalize(omel.speechlike(seconds, seed))
     return a, omel.mel_tensor_from_audio(a)
@@ -104,6 +111,35 @@ def test_transcribe_streaming_token_parity(vx, tiny_model, tiny_oracle):
     tiny_model.debug("tc_off")
     assert tiny_model.transcribe_streaming(mel) == exp
     tiny_model.debug("tc_on")
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3, 5, 8])
+def test_persistent_decode_kernel_matches_per_op_launches(vx, tiny_model8, tiny_oracle, batch):
+    """decode_mega.cu (one persistent kernel per decode step; default) against the per-op launch path
+    and the oracle: same ids for every batch size / token-capacity instantiation (1, 2, 4, 8), and the
+    last step's logits agree to f32 summation-order noise."""
+    sigs = np.stack([omel.speechlike(3.5, seed=40 + i) for i in range(batch)])
+    t_embed = omel.time_embedding(6.0, tiny_oracle.cfg.dec_dim)
+    exp = [tiny_oracle.transcribe_streaming(omel.mel_tensor_from_audio(omel.peak_normalize(s)), t_embed) for s in sigs]
+    tiny_model8.debug("mega_on")
+    n0 = tiny_model8.launch_count()
+    got = tiny_model8.transcribe_pcm(sigs)
+    n_mega = tiny_model8.launch_count() - n0
+    lg_mega = tiny_model8.debug("logits").copy()
+    tiny_model8.debug("mega_off")
+    try:
+        n0 = tiny_model8.launch_count()
+        ref = tiny_model8.transcribe_pcm(sigs)
+        n_ops = tiny_model8.launch_count() - n0
+        lg_ops = tiny_model8.debug("logits").copy()
+    finally:
+        tiny_model8.debug("mega_on")
+    for i in range(batch):
+        assert got[i].tolist() == exp[i], i
+    assert np.array_equal(got, ref)
+    assert n_mega < n_ops  # the persistent kernel really replaced the per-op launches
+    v = tiny_oracle.cfg.vocab
+    assert np.abs(lg_mega[:batch * v] - lg_ops[:batch * v]).max() < 1e-4 * max(1.0, np.abs(lg_ops[:batch * v]).max())
 
 
 def test_transcribe_short_audio_returns_empty(tiny_model):

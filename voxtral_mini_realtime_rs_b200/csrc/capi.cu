@@ -688,6 +688,11 @@ int32_t vox_session_debug_read(vox_session *sh, const char *what, float *out, si
         s->use_gemm_tc = (w == "gemm_tc");
         if (n_floats) *n_floats = 0;
         return VOX_OK;
+    } else if (w == "mega_off" || w == "mega_on") {
+        s->use_mega = (w == "mega_on");
+        if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
+        if (n_floats) *n_floats = 0;
+        return VOX_OK;
     } else if (w == "tc_off" || w == "tc_on") {
         s->use_tc = (w == "tc_on");
         if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }

@@ -1,0 +1,713 @@
+// decode_mega.cu -- one autoregressive decode step for B <= 8 streams as ONE persistent kernel
+// (reference src/gguf/model.rs:938-960 generate_step: embed(prev token) + audio[pos], 26 decoder
+// layers forward_with_cache (model.rs:125-197, 250-255, 665-677), tied lm_head (680-691), argmax).
+//
+// Why: as separate launches the step is 134 dependent kernels of ~11 us each whose weight streams
+// last 1-5 us (profiles/README.md, r01b): launch gaps, per-kernel activation staging and CTA-wide
+// barriers dominate.  Here one CTA per SM lives for the whole step:
+//
+//   * 16 consumer warps + 1 producer warp.  The producer thread walks the step's entire weight
+//     schedule (every matvec of every layer, in order) and streams this CTA's share through a ring
+//     of TMA bulk-copy stages (16 block pairs = 9 KB each, full/empty mbarriers).  It never waits
+//     for activations, so the HBM stream runs ahead across op boundaries: while the consumers sit
+//     in a grid barrier or stage the next op's activations, the ring (100-180 KB) keeps filling.
+//   * a phase (op) = embed | matvec | attention | argmax; consecutive phases are separated by a
+//     grid barrier (one atomic arrival per CTA, acquire spin by one thread).
+//   * matvec arithmetic is matvec_tc.cu's: Q4 nibbles enter mma.sync.m16n8k16 as f16 subnormals,
+//     activations as per-block power-of-two scaled f16 hi+mid pieces, the block scale d applied to
+//     the f32 block sum (shader.wgsl:96-127 re-associated).  A CTA owns whole 16-row tiles
+//     (tile = cta, cta+grid, ...): the 16 warps take one block pair each of every stage, partial sums
+//     meet in shared memory once per tile (ONE named barrier per tile, double-buffered), 16*M
+//     threads add them in fixed warp order and run the epilogue (bias / residual + sums of squares
+//     for the next fused RMSNorm / SiLU*up / running argmax) => no atomics, no split-K scratch,
+//     bitwise deterministic.  When the activation fragments of all of K do not fit shared memory
+//     (M > 2 and K > 3072) the CTA walks K in private slices and keeps tile sums in shared memory.
+//   * attention: RoPE + KV append + GQA as in decode_attn.cu, one CTA per (stream, kv head).
+//
+// All activations written by other CTAs are read with ld.global.cg (L1 is not coherent).
+// Every spin loop has a watchdog that traps instead of hanging the GPU.
+#include <cuda_fp16.h>
+
+#include <cfloat>
+#include <cstdlib>
+
+#include "common.h"
+#include "decode_mega.h"
+#include "kernels.h"
+
+namespace vox {
+
+void tc_count_launch(const char *name);
+
+namespace {
+
+inline void cuda_check_mg(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) fail(VOX_ECUDA, fmt("CUDA error: %s: %s", what, cudaGetErrorString(e)));
+}
+
+constexpr int MG_CWARPS = 16;                    // consumer warps
+constexpr int MG_CTHREADS = MG_CWARPS * 32;
+constexpr int MG_THREADS = MG_CTHREADS + 32;     // + the producer warp
+constexpr int MG_CHUNK = 16;                     // block pairs per ring stage (one per consumer warp)
+constexpr int MG_STAGE_Q = MG_CHUNK * 512;       // nibble bytes of a stage; scales follow
+constexpr int MG_STAGE_BYTES = MG_CHUNK * 576;
+constexpr int MG_MAX_STAGES = 24;
+constexpr int MG_ACC_TILES = 4;                  // tiles per CTA whose sums may persist across K slices
+constexpr int MG_SMEM_MAX = 227 * 1024;
+constexpr int MG_SCRATCH_CAP = 104448;           // 48 pairs at 8 tokens
+constexpr long long MG_SPIN_CYCLES = 4000000000ll;  // ~2 s: watchdog
+
+__host__ __device__ constexpr int mg_misc_bytes(int MT) { return ((416 + 2304 * MT) + 127) & ~127; }
+__host__ __device__ constexpr int mg_pair_bytes(int MT) { return 272 * MT; }  // fragments + offsets of one block pair
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void mg_die(unsigned *flag, unsigned code) {
+    atomicExch(flag, code);
+    __threadfence_system();
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsigned *flag, unsigned code) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    unsigned n = 0;
+    while (!mbar_try(bar, parity)) {
+        if ((++n & 0x3FFFu) == 0 && clock64() - t0 > MG_SPIN_CYCLES) mg_die(flag, code);
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// barrier among the 512 consumer threads (the producer warp never joins)
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t a0, const uint32_t a1, const uint32_t a2,
+                                         const uint32_t a3, const uint32_t b0, const uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ void amax_combine(float &bv, int &bx, const float ov, const int ox) {
+    if (ov > bv || (ov == bv && ox < bx)) { bv = ov; bx = ox; }
+}
+
+__device__ __forceinline__ float4 eff4(const float4 v, const float rinv, const float *gamma, const float *ada, const int k) {
+    if (!gamma) return v;
+    const float4 g = *reinterpret_cast<const float4 *>(gamma + k);
+    float4 o = make_float4((v.x * rinv) * g.x, (v.y * rinv) * g.y, (v.z * rinv) * g.z, (v.w * rinv) * g.w);
+    if (ada) {
+        const float4 a = *reinterpret_cast<const float4 *>(ada + k);
+        o.x *= a.x; o.y *= a.y; o.z *= a.z; o.w *= a.w;
+    }
+    return o;
+}
+
+// Activation side of blocks [b0, b0+nb) -> shared memory (same encoding as matvec_tc.cu tc_stage):
+//   bf   : uint2  [nb][2 (nibble half)][2*MT cols][4 t]   B fragments of lane (g = col, t)
+//   off2 : float2 [nb][MT]   { -8 * sum_{k in block} x , 2^24 / block scale }
+// Rows >= B (capacity padding) and blocks beyond K stage as zeros.
+template <int MT>
+__device__ __forceinline__ void mg_stage(const float *__restrict__ x, const int K, const int B, const float *gamma,
+                                         const float *ada, const int b0, const int nb, const float *__restrict__ rinv,
+                                         uint2 *__restrict__ bf, float2 *__restrict__ off2) {
+    const int items = nb * MT * 4;
+    constexpr int U = 2;
+    for (int base = 0; base < items; base += MG_CTHREADS * U) {
+        float4 lo[U], hi[U];
+        int mm[U], bl[U];
+        bool act[U], ld[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * MG_CTHREADS + (int)threadIdx.x;
+            act[u] = i < items;
+            mm[u] = act[u] ? (i >> 2) % MT : 0;
+            bl[u] = act[u] ? (i >> 2) / MT : 0;
+            const int kb = (b0 + bl[u]) * 32, t = i & 3;
+            lo[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            hi[u] = lo[u];
+            ld[u] = act[u] && kb < K && mm[u] < B;
+            if (ld[u]) {
+                lo[u] = __ldcg(reinterpret_cast<const float4 *>(x + (size_t)mm[u] * K + kb + 4 * t));
+                hi[u] = __ldcg(reinterpret_cast<const float4 *>(x + (size_t)mm[u] * K + kb + 16 + 4 * t));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * MG_CTHREADS + (int)threadIdx.x;
+            const int t = i & 3, m = mm[u];
+            const int kb = (b0 + bl[u]) * 32;
+            float4 l = lo[u], h = hi[u];
+            if (ld[u]) {
+                l = eff4(l, rinv[m], gamma, ada, kb + 4 * t);
+                h = eff4(h, rinv[m], gamma, ada, kb + 16 + 4 * t);
+            }
+            float bs = ((l.x + l.y) + (l.z + l.w)) + ((h.x + h.y) + (h.z + h.w));
+            float bm = fmaxf(fmaxf(fmaxf(fabsf(l.x), fabsf(l.y)), fmaxf(fabsf(l.z), fabsf(l.w))),
+                             fmaxf(fmaxf(fabsf(h.x), fabsf(h.y)), fmaxf(fabsf(h.z), fabsf(h.w))));
+            bs += __shfl_xor_sync(0xffffffffu, bs, 1);
+            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+            bs += __shfl_xor_sync(0xffffffffu, bs, 2);
+            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+            if (!act[u]) continue;
+            int e = (int)((__float_as_uint(bm) >> 23) & 0xFF) - 127;
+            if (!(bm > 0.0f) || bm > 3.0e38f) e = 7;  // all-zero (or non-finite) block: scale 1
+            e = e < -100 ? -100 : (e > 100 ? 100 : e);
+            const float s = __uint_as_float((uint32_t)(7 - e + 127) << 23);
+            const float inv = __uint_as_float((uint32_t)(17 + e + 127) << 23);  // 2^24 / s
+            const float ev[8] = {l.x * s, l.y * s, l.z * s, l.w * s,
+                                 h.x * s * 0.0625f, h.y * s * 0.0625f, h.z * s * 0.0625f, h.w * s * 0.0625f};
+            float hh[8], md[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                hh[q] = __half2float(__float2half_rn(ev[q]));
+                md[q] = ev[q] - hh[q];
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int o = 4 * j;
+                uint2 fh, fm;
+                fh.x = pack_h2(hh[o + 0], hh[o + 2]);
+                fh.y = pack_h2(hh[o + 1], hh[o + 3]);
+                fm.x = pack_h2(md[o + 0], md[o + 2]);
+                fm.y = pack_h2(md[o + 1], md[o + 3]);
+                uint2 *dst = bf + ((size_t)(bl[u] * 2 + j) * (2 * MT)) * 4;
+                dst[(2 * m + 0) * 4 + t] = fh;
+                dst[(2 * m + 1) * 4 + t] = fm;
+            }
+            if (t == 0) off2[bl[u] * MT + m] = make_float2(-8.0f * bs, inv);
+        }
+    }
+}
+
+template <int MT, int G, int DPL>
+__global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaParams p) {
+    constexpr int CG = (MT + 3) / 4;
+    constexpr int HD = DPL * 32;
+    constexpr int RW = (16 * MT + 31) / 32;  // warps that add the per-warp partial sums and run the epilogue
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + MG_MAX_STAGES;
+    float *rinv = reinterpret_cast<float *>(empty + MG_MAX_STAGES);   // [8]
+    float *red = rinv + 8;                                            // [2][MG_CWARPS][16*MT]
+    float *acc_tile = red + 2 * MG_CWARPS * 16 * MT;                  // [MG_ACC_TILES][16*MT]
+    unsigned char *scratch = smem + mg_misc_bytes(MT);
+    unsigned char *ring = scratch + p.scratch_bytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int cta = blockIdx.x, nctas = gridDim.x;
+    const int B = p.B, nstage = p.nstage;
+    unsigned *wd_flag = p.bar + 2;
+
+    if (tid == 0) {
+        for (int i = 0; i < nstage; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], MG_CWARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    // =========================== producer: the step's whole weight schedule ===========================
+    if (warp == MG_CWARPS) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool wrapped = false;
+            for (int oi = 0; oi < p.n_ops; ++oi) {
+                const MegaOp &op = p.ops[oi];
+                if (op.kind != MG_MATVEC) continue;
+                const int n_tiles = op.n_tiles, n_pairs = op.n_pairs, S = op.S, Ps = op.Ps;
+                const uint4 *qs = op.qs_tc;
+                const uint2 *ds = op.d_tc;
+                const int ntl = cta < n_tiles ? (n_tiles - cta + nctas - 1) / nctas : 0;
+                for (int s = 0; s < S; ++s) {
+                    const int pb = s * Ps;
+                    const int np = min(Ps, n_pairs - pb);
+                    for (int it = 0; it < ntl; ++it) {
+                        const int tile = cta + it * nctas;
+                        for (int c0 = 0; c0 < np; c0 += MG_CHUNK) {
+                            const int nb = min(MG_CHUNK, np - c0);
+                            if (wrapped) mbar_wait(&empty[stage], phase ^ 1u, wd_flag, 0x100u + (unsigned)oi);
+                            unsigned char *dst = ring + (size_t)stage * MG_STAGE_BYTES;
+                            mbar_expect_tx(&full[stage], (uint32_t)nb * 576u);
+                            const size_t pair0 = (size_t)tile * n_pairs + pb + c0;
+                            bulk_g2s(dst, qs + pair0 * 32, (uint32_t)nb * 512u, &full[stage]);
+                            bulk_g2s(dst + MG_STAGE_Q, ds + pair0 * 8, (uint32_t)nb * 64u, &full[stage]);
+                            if (++stage == nstage) {
+                                stage = 0;
+                                phase ^= 1u;
+                                wrapped = true;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // =========================== consumers ===========================
+    const int pos = *p.d_pos;
+    const int outpos = *p.d_outpos;
+    int stage = 0;
+    uint32_t phase = 0;
+    int par = 0;
+    unsigned bar_target = 0;
+    float best_v = -INFINITY;
+    int best_i = 0x7fffffff;
+
+    for (int oi = 0; oi < p.n_ops; ++oi) {
+        const MegaOp &op = p.ops[oi];
+        const int kind = op.kind;
+        if (kind == MG_MATVEC) {
+            const int n_tiles = op.n_tiles, n_pairs = op.n_pairs, S = op.S, Ps = op.Ps, N = op.N, K = op.K;
+            const int epi = op.epi, ldy = op.ldy, track = op.track_argmax;
+            float *const yout = op.y;
+            const float *const bias = op.bias, *const resid = op.res;
+            float *const ssq_out = op.ssq_out;
+            const int ntl = cta < n_tiles ? (n_tiles - cta + nctas - 1) / nctas : 0;
+            float2 *off2 = reinterpret_cast<float2 *>(scratch);             // [2*Ps][MT]
+            uint2 *bf = reinterpret_cast<uint2 *>(off2 + (size_t)Ps * 2 * MT);  // [2*Ps][2][2*MT][4]
+            if (ntl > 0) {
+                for (int s = 0; s < S; ++s) {
+                    const int pb = s * Ps;
+                    const int np = min(Ps, n_pairs - pb);
+                    if (s == 0 && op.gamma && warp < B) {
+                        float ss = 0.0f;
+                        for (int i = lane; i < op.ssq_in_parts; i += 32) ss += __ldcg(op.ssq_in + (size_t)i * B + warp);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                        if (lane == 0) rinv[warp] = 1.0f / sqrtf(ss / (float)K + p.eps);
+                    }
+                    cbar();  // rinv visible; every warp is done with the previous contents of scratch
+                    mg_stage<MT>(op.x, K, B, op.gamma, op.ada, pb * 2, np * 2, rinv, bf, off2);
+                    cbar();
+                    for (int it = 0; it < ntl; ++it) {
+                        const int tile = cta + it * nctas;
+                        float acc[CG][2];
+#pragma unroll
+                        for (int c = 0; c < CG; ++c) acc[c][0] = acc[c][1] = 0.0f;
+                        for (int c0 = 0; c0 < np; c0 += MG_CHUNK) {
+                            mbar_wait(&full[stage], phase, wd_flag, 0x200u + (unsigned)oi);
+                            const int pp = c0 + warp;  // pair index inside the slice
+                            if (pp < np) {
+                                const unsigned char *sb = ring + (size_t)stage * MG_STAGE_BYTES;
+                                const uint4 wq = reinterpret_cast<const uint4 *>(sb)[warp * 32 + lane];
+                                const uint2 wd = reinterpret_cast<const uint2 *>(sb + MG_STAGE_Q)[warp * 8 + g];
+                                const uint32_t words[2][2] = {{wq.x, wq.y}, {wq.z, wq.w}};
+                                const __half2 dlo = *reinterpret_cast<const __half2 *>(&wd.x);
+                                const __half2 dhi = *reinterpret_cast<const __half2 *>(&wd.y);
+                                const float dsc[2][2] = {{__low2float(dlo), __high2float(dlo)},
+                                                         {__low2float(dhi), __high2float(dhi)}};
+#pragma unroll
+                                for (int bb = 0; bb < 2; ++bb) {
+                                    const int bl = pp * 2 + bb;
+                                    const uint32_t wg = words[bb][0], wg8 = words[bb][1];
+                                    const uint32_t sg = wg >> 8, sg8 = wg8 >> 8;
+                                    const uint32_t a_lo[4] = {wg & 0x000F000Fu, wg8 & 0x000F000Fu, sg & 0x000F000Fu, sg8 & 0x000F000Fu};
+                                    const uint32_t a_hi[4] = {wg & 0x00F000F0u, wg8 & 0x00F000F0u, sg & 0x00F000F0u, sg8 & 0x00F000F0u};
+                                    const uint2 *bfb = bf + (size_t)(bl * 2) * (2 * MT) * 4;
+#pragma unroll
+                                    for (int c = 0; c < CG; ++c) {
+                                        const int col = c * 8 + g;
+                                        uint2 blo = make_uint2(0u, 0u), bhi = blo;
+                                        if (col < 2 * MT) {
+                                            blo = bfb[col * 4 + t];
+                                            bhi = bfb[(2 * MT + col) * 4 + t];
+                                        }
+                                        float cc[4] = {0.f, 0.f, 0.f, 0.f};
+                                        mma16816(cc, a_lo[0], a_lo[1], a_lo[2], a_lo[3], blo.x, blo.y);
+                                        mma16816(cc, a_hi[0], a_hi[1], a_hi[2], a_hi[3], bhi.x, bhi.y);
+                                        const int tok = c * 4 + t;
+                                        const float2 o = tok < MT ? off2[bl * MT + tok] : make_float2(0.0f, 0.0f);
+                                        acc[c][0] = fmaf(dsc[bb][0], fmaf(cc[0] + cc[1], o.y, o.x), acc[c][0]);
+                                        acc[c][1] = fmaf(dsc[bb][1], fmaf(cc[2] + cc[3], o.y, o.x), acc[c][1]);
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&empty[stage]);
+                            if (++stage == nstage) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                        // ---- the 16 warps' partial sums of this tile meet in shared memory
+                        float *rw = red + (size_t)(par * MG_CWARPS + warp) * 16 * MT;
+#pragma unroll
+                        for (int c = 0; c < CG; ++c) {
+                            const int tok = c * 4 + t;
+                            if (tok < MT) {
+                                rw[tok * 16 + g] = acc[c][0];
+                                rw[tok * 16 + g + 8] = acc[c][1];
+                            }
+                        }
+                        cbar();
+                        if (warp < RW) {
+                            const int i = tid;
+                            const bool valid = i < 16 * MT;
+                            const int tok = i >> 4, r = i & 15;
+                            const int row = tile * 16 + r;
+                            float v = 0.0f;
+                            if (valid) {
+                                const float *rp = red + (size_t)par * MG_CWARPS * 16 * MT + i;
+#pragma unroll
+                                for (int w = 0; w < MG_CWARPS; ++w) v += rp[w * 16 * MT];
+                                if (S > 1) {
+                                    float *at = acc_tile + (size_t)it * 16 * MT + i;
+                                    if (s > 0) v += *at;
+                                    if (s + 1 < S) *at = v;
+                                }
+                            }
+                            if (s + 1 == S) {
+                                const bool live = valid && tok < B;
+                                if (epi == EPI_SILU_MUL) {
+                                    const float o = __shfl_xor_sync(0xffffffffu, v, 1);
+                                    if (live && !(r & 1) && row + 1 < N)
+                                        yout[(size_t)tok * ldy + (row >> 1)] = (v / (1.0f + expf(-v))) * o;
+                                } else {
+                                    float out = 0.0f;
+                                    if (live && row < N) {
+                                        out = v + (bias ? bias[row] : 0.0f);
+                                        if (epi == EPI_RESIDUAL) out += __ldcg(resid + (size_t)tok * ldy + row);
+                                        if (epi == EPI_GELU) out = 0.5f * out * (1.0f + erff(out * 0.70710678118654752440f));
+                                        yout[(size_t)tok * ldy + row] = out;
+                                        if (track) amax_combine(best_v, best_i, out, row);
+                                    }
+                                    if (ssq_out) {
+                                        float sq = out * out;
+                                        sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+                                        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                                        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                                        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                                        if (live && r == 0) ssq_out[(size_t)tile * B + tok] = sq;
+                                    }
+                                }
+                            }
+                        }
+                        par ^= 1;
+                    }
+                }
+            }
+            if (track && warp < RW) {
+                // this CTA's best candidate per stream (lowest index wins ties: order independent)
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+                    const int ox = __shfl_xor_sync(0xffffffffu, best_i, o);
+                    amax_combine(best_v, best_i, ov, ox);
+                }
+                const int tok = tid >> 4;
+                if ((tid & 15) == 0 && tok < B) {
+                    p.am_vals[(size_t)cta * 8 + tok] = best_v;
+                    p.am_idx[(size_t)cta * 8 + tok] = best_i;
+                }
+                best_v = -INFINITY;
+                best_i = 0x7fffffff;
+            }
+        } else if (kind == MG_ATTN) {
+            float *qs = reinterpret_cast<float *>(scratch);       // [G][HD]
+            float *kvs = qs + G * HD;                              // [2][HD]
+            float *red_m = kvs + 2 * HD;                           // [MG_CWARPS][G]
+            float *red_l = red_m + MG_CWARPS * G;                  // [MG_CWARPS][G]
+            float *red_acc = red_l + MG_CWARPS * G;                // [MG_CWARPS][G][HD]
+            const int H = p.H, Hkv = p.Hkv, max_seq = p.max_seq;
+            for (int unit = cta; unit < B * Hkv && pos < max_seq; unit += nctas) {
+                const int b = unit / Hkv, kvh = unit - b * Hkv;
+                const float *row = p.qkv + (size_t)b * p.ld_qkv;
+                cbar();  // scratch free (previous unit / previous op)
+                for (int i = tid; i < G * HD; i += MG_CTHREADS) qs[i] = __ldcg(row + (size_t)(kvh * G) * HD + i);
+                for (int i = tid; i < HD; i += MG_CTHREADS) {
+                    kvs[i] = __ldcg(row + (size_t)H * HD + kvh * HD + i);
+                    kvs[HD + i] = __ldcg(row + (size_t)(H + Hkv) * HD + kvh * HD + i);
+                }
+                cbar();
+                constexpr int half = HD / 2;
+                for (int i = tid; i < (G + 1) * half; i += MG_CTHREADS) {
+                    const int h = i / half, pi = i - h * half;
+                    float *v = (h < G) ? &qs[h * HD + 2 * pi] : &kvs[2 * pi];
+                    const float c = p.cos_t[(size_t)pos * half + pi], sn = p.sin_t[(size_t)pos * half + pi];
+                    const float xr = v[0], xi = v[1];
+                    v[0] = xr * c - xi * sn;
+                    v[1] = xr * sn + xi * c;
+                }
+                cbar();
+                float *kbase = op.kc + ((size_t)b * Hkv + kvh) * max_seq * HD;
+                float *vbase = op.vc + ((size_t)b * Hkv + kvh) * max_seq * HD;
+                for (int i = tid; i < HD; i += MG_CTHREADS) {
+                    kbase[(size_t)pos * HD + i] = kvs[i];
+                    vbase[(size_t)pos * HD + i] = kvs[HD + i];
+                }
+                float q[G][DPL];
+#pragma unroll
+                for (int h = 0; h < G; ++h)
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) q[h][i] = qs[h * HD + lane * DPL + i];
+                float m_run[G], l_run[G], acc[G][DPL];
+#pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    m_run[h] = -INFINITY;
+                    l_run[h] = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) acc[h][i] = 0.0f;
+                }
+                const int j_lo = pos - p.window > 0 ? pos - p.window : 0;
+                for (int j = j_lo + warp; j <= pos; j += MG_CWARPS) {
+                    float kk[DPL], vv[DPL];
+                    if (j == pos) {  // the row appended above: take it from shared memory
+#pragma unroll
+                        for (int i = 0; i < DPL; ++i) {
+                            kk[i] = kvs[lane * DPL + i];
+                            vv[i] = kvs[HD + lane * DPL + i];
+                        }
+                    } else {
+                        const float *kr = kbase + (size_t)j * HD + lane * DPL;
+                        const float *vr = vbase + (size_t)j * HD + lane * DPL;
+#pragma unroll
+                        for (int i = 0; i < DPL; ++i) {
+                            kk[i] = kr[i];
+                            vv[i] = vr[i];
+                        }
+                    }
+                    float sc[G];
+#pragma unroll
+                    for (int h = 0; h < G; ++h) {
+                        float d = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < DPL; ++i) d = fmaf(q[h][i], kk[i], d);
+                        sc[h] = d;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int h = 0; h < G; ++h) sc[h] += __shfl_xor_sync(0xffffffffu, sc[h], o);
+#pragma unroll
+                    for (int h = 0; h < G; ++h) {
+                        const float s1 = sc[h] * p.scale;
+                        const float m_new = fmaxf(m_run[h], s1);
+                        const float alpha = expf(m_run[h] - m_new);
+                        const float pe = expf(s1 - m_new);
+                        l_run[h] = l_run[h] * alpha + pe;
+                        m_run[h] = m_new;
+#pragma unroll
+                        for (int i = 0; i < DPL; ++i) acc[h][i] = fmaf(pe, vv[i], acc[h][i] * alpha);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    if (lane == 0) {
+                        red_m[warp * G + h] = m_run[h];
+                        red_l[warp * G + h] = l_run[h];
+                    }
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) red_acc[((size_t)warp * G + h) * HD + lane * DPL + i] = acc[h][i];
+                }
+                cbar();
+                for (int i = tid; i < G * HD; i += MG_CTHREADS) {
+                    const int h = i / HD, d = i - h * HD;
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int w = 0; w < MG_CWARPS; ++w) mx = fmaxf(mx, red_m[w * G + h]);
+                    float num = 0.0f, den = 0.0f;
+#pragma unroll
+                    for (int w = 0; w < MG_CWARPS; ++w) {
+                        const float mw = red_m[w * G + h];
+                        const float f = (mw == -INFINITY) ? 0.0f : expf(mw - mx);
+                        num = fmaf(red_acc[((size_t)w * G + h) * HD + d], f, num);
+                        den = fmaf(red_l[w * G + h], f, den);
+                    }
+                    p.attn_out[(size_t)b * (H * HD) + (size_t)(kvh * G + h) * HD + d] = num / den;
+                }
+            }
+        } else if (kind == MG_EMBED) {
+            // x_dec[b] = audio[b][pos] + dequant(E[tok[b]])   (model.rs:584-618, 938-946)
+            const int D = p.D, bpr = D >> 5, n = bpr * 16;
+            for (int b = cta; b < B; b += nctas) {
+                const int id = p.d_tok[b];
+                const float *arow = p.audio ? p.audio + ((size_t)b * p.audio_seq + pos) * D : nullptr;
+                for (int base = 0; base < n; base += MG_CTHREADS) {
+                    const int i = base + tid;
+                    const bool act = i < n;
+                    const int blk = i >> 4, j = i & 15;
+                    float lo = 0.0f, hi = 0.0f;
+                    if (act) {
+                        const uint8_t byte = reinterpret_cast<const uint8_t *>(p.emb_qs + (size_t)id * bpr + blk)[j];
+                        const float dd = __half2float(p.emb_d[(size_t)id * bpr + blk]);
+                        const int k = blk * 32 + j;
+                        lo = ((float)(byte & 0xF) - 8.0f) * dd;
+                        hi = ((float)(byte >> 4) - 8.0f) * dd;
+                        if (arow) {
+                            lo = arow[k] + lo;
+                            hi = arow[k + 16] + hi;
+                        }
+                        p.x_dec[(size_t)b * D + k] = lo;
+                        p.x_dec[(size_t)b * D + k + 16] = hi;
+                    }
+                    float sl = lo * lo, sh = hi * hi;
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) {
+                        sl += __shfl_xor_sync(0xffffffffu, sl, o);
+                        sh += __shfl_xor_sync(0xffffffffu, sh, o);
+                    }
+                    if (act && j == 0) {
+                        p.ssq_x[(size_t)(2 * blk) * B + b] = sl;
+                        p.ssq_x[(size_t)(2 * blk + 1) * B + b] = sh;
+                    }
+                }
+            }
+        } else {  // MG_ARGMAX
+            if (cta == 0) {
+                if (warp < B) {
+                    float bv = -INFINITY;
+                    int bx = 0x7fffffff;
+                    for (int c = lane; c < nctas; c += 32)
+                        amax_combine(bv, bx, __ldcg(p.am_vals + (size_t)c * 8 + warp), __ldcg(p.am_idx + (size_t)c * 8 + warp));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                        const int ox = __shfl_xor_sync(0xffffffffu, bx, o);
+                        amax_combine(bv, bx, ov, ox);
+                    }
+                    if (lane == 0) {
+                        if (bx == 0x7fffffff) bx = 0;
+                        p.d_tok[warp] = bx;
+                        if (p.d_out) p.d_out[(size_t)warp * p.out_ld + outpos] = bx;
+                    }
+                }
+                if (tid == 0) {
+                    *p.d_pos = pos + 1;
+                    *p.d_outpos = outpos + 1;
+                }
+            }
+        }
+        // ---- grid barrier between phases
+        if (oi + 1 < p.n_ops) {
+            cbar();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(&p.bar[0], 1u);
+                bar_target += (unsigned)nctas;
+                const long long t0 = clock64();
+                unsigned n = 0;
+                while (ld_acquire_u32(&p.bar[0]) < bar_target) {
+                    if ((++n & 0x3FFu) == 0 && clock64() - t0 > MG_SPIN_CYCLES) mg_die(wd_flag, 0x300u + (unsigned)oi);
+                }
+                __threadfence();
+            }
+            cbar();
+        }
+    }
+    // the last CTA to finish re-arms the barrier for the next launch
+    if (tid == 0) {
+        __threadfence();
+        const unsigned old = atomicAdd(&p.bar[1], 1u);
+        if (old == (unsigned)nctas - 1u) {
+            p.bar[0] = 0u;
+            p.bar[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+template <int MT, int G, int DPL>
+void launch_t(const MegaParams &p, const MegaPlan &plan, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cuda_check_mg(cudaFuncSetAttribute(decode_mega_kernel<MT, G, DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_MAX),
+                      "cudaFuncSetAttribute(decode_mega)");
+        attr_set = true;
+    }
+    decode_mega_kernel<MT, G, DPL><<<grid, MG_THREADS, plan.smem_bytes, st>>>(p);
+    cuda_check_mg(cudaGetLastError(), "decode_mega launch");
+    tc_count_launch("decode_mega");
+}
+
+template <int MT>
+void launch_m(const MegaParams &p, const MegaPlan &plan, int grid, cudaStream_t st) {
+    const int G = p.H / p.Hkv;
+    if (G == 4 && p.hd == 128) launch_t<MT, 4, 4>(p, plan, grid, st);
+    else if (G == 2 && p.hd == 32) launch_t<MT, 2, 1>(p, plan, grid, st);
+    else fail(VOX_EINVAL, "decode_mega: unsupported attention shape");
+}
+
+}  // namespace
+
+bool decode_mega_supported(int B, int H, int Hkv, int hd) {
+    if (B < 1 || B > 8 || Hkv <= 0 || H % Hkv != 0) return false;
+    const int G = H / Hkv;
+    return (G == 4 && hd == 128) || (G == 2 && hd == 32);
+}
+
+MegaPlan decode_mega_plan(int B, int max_pairs, int H, int Hkv, int hd) {
+    MegaPlan pl;
+    pl.MT = B <= 1 ? 1 : (B <= 2 ? 2 : (B <= 4 ? 4 : 8));
+    const int G = H / Hkv;
+    const int attn_bytes = ((G + 2) * hd + 2 * MG_CWARPS * G + MG_CWARPS * G * hd) * (int)sizeof(float);
+    const int per_pair = mg_pair_bytes(pl.MT);
+    int cap_pairs = MG_SCRATCH_CAP / per_pair;
+    if (cap_pairs >= MG_CHUNK) cap_pairs = cap_pairs / MG_CHUNK * MG_CHUNK;
+    pl.Ps_cap = max_pairs < cap_pairs ? max_pairs : cap_pairs;
+    if (pl.Ps_cap < 1) pl.Ps_cap = 1;
+    int scratch = pl.Ps_cap * per_pair;
+    if (scratch < attn_bytes) scratch = attn_bytes;
+    pl.scratch_bytes = (scratch + 127) & ~127;
+    const int left = MG_SMEM_MAX - mg_misc_bytes(pl.MT) - pl.scratch_bytes;
+    int ns = left / MG_STAGE_BYTES;
+    pl.nstage = ns > MG_MAX_STAGES ? MG_MAX_STAGES : ns;
+    VOX_CHECK(pl.nstage >= 2, VOX_EINVAL, "decode_mega: no room for the weight ring (%d stages)", pl.nstage);
+    pl.smem_bytes = (size_t)mg_misc_bytes(pl.MT) + pl.scratch_bytes + (size_t)pl.nstage * MG_STAGE_BYTES;
+    return pl;
+}
+
+int decode_mega_grid(int device) {
+    int sms = 0;
+    cuda_check_mg(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute(SM count)");
+    return sms;
+}
+
+void launch_decode_mega(const MegaParams &p, const MegaPlan &plan, int grid, cudaStream_t st) {
+    VOX_CHECK(p.nstage == plan.nstage && p.scratch_bytes == plan.scratch_bytes, VOX_EINVAL, "decode_mega: plan mismatch");
+    switch (plan.MT) {
+        case 1: launch_m<1>(p, plan, grid, st); break;
+        case 2: launch_m<2>(p, plan, grid, st); break;
+        case 4: launch_m<4>(p, plan, grid, st); break;
+        case 8: launch_m<8>(p, plan, grid, st); break;
+        default: fail(VOX_EINVAL, "decode_mega: bad token capacity");
+    }
+}
+
+}  // namespace vox

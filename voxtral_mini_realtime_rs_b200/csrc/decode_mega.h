@@ -1,0 +1,84 @@
+// decode_mega.h -- op table of the persistent decode-step kernel (decode_mega.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace vox {
+
+enum MegaKind : int {
+    MG_EMBED = 0,   // x_dec[b] = audio[b][pos-?] + dequant(E[tok[b]])  (+ sums of squares for the first norm)
+    MG_MATVEC = 1,  // y = epi(norm?(x) . W^T), weights streamed through the CTA's TMA ring
+    MG_ATTN = 2,    // RoPE + KV append + GQA attention of one layer
+    MG_ARGMAX = 3,  // combine the per-CTA lm_head candidates, write the token, advance the counters
+};
+
+// One grid-wide phase.  A grid barrier separates consecutive phases.
+struct MegaOp {
+    int kind = 0, epi = 0;
+    // MG_MATVEC
+    const uint4 *qs_tc = nullptr;
+    const uint2 *d_tc = nullptr;
+    int N = 0, K = 0, n_tiles = 0, n_pairs = 0;
+    int S = 1, Ps = 0;  // CTA-private K slices: the activation fragments of one slice fit the scratch region
+    const float *x = nullptr;
+    float *y = nullptr;
+    int ldy = 0;
+    const float *bias = nullptr, *res = nullptr;
+    const float *gamma = nullptr, *ada = nullptr;
+    const float *ssq_in = nullptr;  // [ssq_in_parts][B]
+    int ssq_in_parts = 0;
+    float *ssq_out = nullptr;       // [n_tiles][B]
+    int track_argmax = 0;
+    // MG_ATTN
+    float *kc = nullptr, *vc = nullptr;  // this layer's caches [B][Hkv][max_seq][hd]
+};
+
+struct MegaParams {
+    const MegaOp *ops = nullptr;
+    int n_ops = 0;
+    int B = 0;  // streams (= token rows of every matvec)
+    float eps = 0.f;
+    // attention
+    float *qkv = nullptr;
+    int ld_qkv = 0, H = 0, Hkv = 0, hd = 0, max_seq = 0, window = 0;
+    float scale = 0.f;
+    const float *cos_t = nullptr, *sin_t = nullptr;
+    float *attn_out = nullptr;
+    // embedding (row-major planes of the tied table)
+    const uint4 *emb_qs = nullptr;
+    const __half *emb_d = nullptr;
+    int D = 0;
+    const float *audio = nullptr;
+    int audio_seq = 0;
+    float *x_dec = nullptr, *ssq_x = nullptr;
+    // device-side step state
+    int *d_pos = nullptr, *d_outpos = nullptr, *d_tok = nullptr, *d_out = nullptr;
+    int out_ld = 0;
+    // per-CTA argmax candidates [grid][8]
+    float *am_vals = nullptr;
+    int *am_idx = nullptr;
+    // grid barrier: [0] arrivals, [1] finished CTAs, [2] watchdog code
+    unsigned *bar = nullptr;
+    // shared-memory plan
+    int nstage = 0, scratch_bytes = 0;
+};
+
+struct MegaPlan {
+    int MT = 0;             // token capacity of the instantiation (1, 2, 4, 8)
+    int Ps_cap = 0;         // pairs per K slice that fit the scratch region
+    int scratch_bytes = 0;
+    int nstage = 0;
+    size_t smem_bytes = 0;
+};
+
+// Shapes the persistent kernel is instantiated for.
+bool decode_mega_supported(int B, int H, int Hkv, int hd);
+// Shared-memory plan for B streams given the largest K (in block pairs) of any matvec of the step.
+MegaPlan decode_mega_plan(int B, int max_pairs, int H, int Hkv, int hd);
+int decode_mega_grid(int device);
+void launch_decode_mega(const MegaParams &p, const MegaPlan &plan, int grid, cudaStream_t st);
+
+}  // namespace vox

@@ -469,6 +469,17 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
             s->am_cnt = s->arena.alloc_n<int>(max_batch);
             CUDA_OK(cudaMemset(s->am_cnt, 0, sizeof(int) * max_batch));
         }
+        {   // persistent decode-step kernel
+            const char *mv = getenv("VOX_MEGA");
+            s->use_mega = !(mv && mv[0] == '0');
+            s->mega_grid = decode_mega_grid(m->device);
+            s->mega_ops_cap = 5 * c.dec_layers + 4;
+            s->mega_ops = s->arena.alloc_n<MegaOp>(s->mega_ops_cap);
+            s->mega_bar = s->arena.alloc_n<unsigned>(4);
+            CUDA_OK(cudaMemset(s->mega_bar, 0, sizeof(unsigned) * 4));
+            s->mega_am_vals = s->arena.alloc_n<float>((size_t)s->mega_grid * 8);
+            s->mega_am_idx = s->arena.alloc_n<int>((size_t)s->mega_grid * 8);
+        }
         CUDA_OK(cudaMemset(s->d_pos, 0, sizeof(int)));
         CUDA_OK(cudaMemset(s->d_outpos, 0, sizeof(int)));
         s->set_delay(6.0f);  // CLI default --delay 6 (transcribe.rs:49-51)
@@ -649,10 +660,132 @@ void Session::lm_head_rows(int rows, bool norm_pending, float *dst) {
         linear(m->tok_emb, h_dec, rows, dst, c.vocab, nullptr, nullptr, EPI_NONE);
 }
 
+// Builds (once per batch size) the op table of the persistent decode-step kernel.  Returns false when
+// the shapes are outside what decode_mega.cu is instantiated for; the caller then uses per-op launches.
+bool Session::mega_prepare(int B) {
+    const vox_model_info &c = m->info;
+    if (!use_mega || !use_tc || !fused_decode(B)) return false;
+    if (!decode_mega_supported(B, c.dec_heads, c.dec_kv_heads, c.dec_head_dim)) return false;
+    if (mega_B == B) return mega_n_ops > 0;
+    mega_B = B;
+    mega_n_ops = 0;
+    const int D = c.dec_dim, H = c.dec_heads, Hkv = c.dec_kv_heads, hd = c.dec_head_dim;
+    const int qkvd = (H + 2 * Hkv) * hd;
+    for (int j = 0; j < c.dec_layers; ++j)
+        if (!m->dec[j].wqkv.qs_tc || !m->dec[j].wo.qs_tc || !m->dec[j].w13.qs_tc || !m->dec[j].w2.qs_tc) return false;
+    auto pairs = [](int K) { return (K / 32 + 1) / 2; };
+    const int max_pairs = std::max(std::max(pairs(D), pairs(H * hd)), pairs(c.dec_ffn));
+    mega_plan = decode_mega_plan(B, max_pairs, H, Hkv, hd);
+    const size_t layer_stride = (size_t)max_batch * Hkv * out_ld * hd;
+    const int parts = (D + 15) / 16;
+    std::vector<MegaOp> ops;
+    bool ok = true;
+    auto matvec = [&](const Q4Weight &w, const float *x, float *y, int ldy, const float *res, int epi, const float *gamma,
+                      const float *ada_v, bool ssq_out_, bool track) {
+        MegaOp o;
+        o.kind = MG_MATVEC;
+        o.epi = epi;
+        o.qs_tc = w.qs_tc;
+        o.d_tc = w.d_tc;
+        o.N = w.N;
+        o.K = w.K;
+        o.n_tiles = (w.N + 15) / 16;
+        o.n_pairs = pairs(w.K);
+        int S = (o.n_pairs + mega_plan.Ps_cap - 1) / mega_plan.Ps_cap;
+        int Ps = (o.n_pairs + S - 1) / S;
+        if (S > 1) Ps = std::min(mega_plan.Ps_cap, (Ps + 15) / 16 * 16);
+        S = (o.n_pairs + Ps - 1) / Ps;
+        o.S = S;
+        o.Ps = Ps;
+        if (S > 1 && (o.n_tiles + mega_grid - 1) / mega_grid > 4) ok = false;  // tile sums kept across slices: 4 per CTA
+        o.x = x;
+        o.y = y;
+        o.ldy = ldy;
+        o.res = res;
+        o.gamma = gamma;
+        o.ada = ada_v;
+        if (gamma) {
+            o.ssq_in = ssq_x;
+            o.ssq_in_parts = parts;
+        }
+        if (ssq_out_) o.ssq_out = ssq_x;
+        o.track_argmax = track ? 1 : 0;
+        ops.push_back(o);
+    };
+    {
+        MegaOp e;
+        e.kind = MG_EMBED;
+        ops.push_back(e);
+    }
+    for (int j = 0; j < c.dec_layers; ++j) {
+        const DecLayerW &l = m->dec[j];
+        matvec(l.wqkv, x_dec, qkv_dec, qkvd, nullptr, EPI_NONE, l.attn_norm, nullptr, false, false);
+        MegaOp a;
+        a.kind = MG_ATTN;
+        a.kc = kc + (size_t)j * layer_stride;
+        a.vc = vc + (size_t)j * layer_stride;
+        ops.push_back(a);
+        matvec(l.wo, attn_dec, x_dec, D, x_dec, EPI_RESIDUAL, nullptr, nullptr, true, false);
+        matvec(l.w13, x_dec, act_dec, c.dec_ffn, nullptr, EPI_SILU_MUL, l.ffn_norm, ada + (size_t)j * D, false, false);
+        matvec(l.w2, act_dec, x_dec, D, x_dec, EPI_RESIDUAL, nullptr, nullptr, true, false);
+    }
+    matvec(m->tok_emb, x_dec, logits, c.vocab, nullptr, EPI_NONE, m->dec_norm, nullptr, false, true);
+    {
+        MegaOp f;
+        f.kind = MG_ARGMAX;
+        ops.push_back(f);
+    }
+    // the residual epilogues and the embedding must leave exactly `parts` partial sums of squares
+    if ((D + 15) / 16 != parts || D % 32 != 0) ok = false;
+    if (!ok || (int)ops.size() > mega_ops_cap) return false;
+    mega_ops_host = ops;
+    CUDA_OK(cudaMemcpyAsync(mega_ops, mega_ops_host.data(), sizeof(MegaOp) * ops.size(), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    mega_n_ops = (int)ops.size();
+    return true;
+}
+
 // One autoregressive step for B streams (model.rs:938-960): embed(prev token) + audio[pos-1],
 // 26 layers, lm_head, argmax, device-side feedback; all positions read from device counters.
 void Session::decode_step(int B) {
     const vox_model_info &c = m->info;
+    if (mega_prepare(B)) {
+        MegaParams p;
+        p.ops = mega_ops;
+        p.n_ops = mega_n_ops;
+        p.B = B;
+        p.eps = m->norm_eps;
+        p.qkv = qkv_dec;
+        p.ld_qkv = (c.dec_heads + 2 * c.dec_kv_heads) * c.dec_head_dim;
+        p.H = c.dec_heads;
+        p.Hkv = c.dec_kv_heads;
+        p.hd = c.dec_head_dim;
+        p.max_seq = out_ld;
+        p.window = c.dec_window;
+        p.scale = powf((float)c.dec_head_dim, -0.5f);
+        p.cos_t = m->dec_cos;
+        p.sin_t = m->dec_sin;
+        p.attn_out = attn_dec;
+        p.emb_qs = m->tok_emb.qs;
+        p.emb_d = m->tok_emb.d;
+        p.D = c.dec_dim;
+        p.audio = audio;
+        p.audio_seq = cur_S4;
+        p.x_dec = x_dec;
+        p.ssq_x = ssq_x;
+        p.d_pos = d_pos;
+        p.d_outpos = d_outpos;
+        p.d_tok = d_tok;
+        p.d_out = d_out;
+        p.out_ld = out_ld;
+        p.am_vals = mega_am_vals;
+        p.am_idx = mega_am_idx;
+        p.bar = mega_bar;
+        p.nstage = mega_plan.nstage;
+        p.scratch_bytes = mega_plan.scratch_bytes;
+        launch_decode_mega(p, mega_plan, mega_grid, st);
+        return;
+    }
     launch_embed(m->tok_emb, d_tok, audio, cur_S4, B, 1, d_pos, x_dec, fused_decode(B) ? ssq_x : nullptr, st);
     const bool pending = decoder_forward(B, 1);
     lm_head_rows(B, pending, logits);

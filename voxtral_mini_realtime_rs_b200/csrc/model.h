@@ -9,6 +9,7 @@
 
 #include "audio_host.h"
 #include "gguf.h"
+#include "decode_mega.h"
 #include "kernels.h"
 
 namespace vox {
@@ -119,6 +120,17 @@ struct Session {
     float *am_vals = nullptr;
     int *am_idx = nullptr, *am_cnt = nullptr;
     TcWork tc_work(bool norm_in, bool ssq_out) const;
+    // persistent decode-step kernel (decode_mega.cu): op table per batch size, grid barrier words,
+    // per-CTA argmax candidates.  VOX_MEGA=0 (or debug "mega_off") selects the per-op launches.
+    bool use_mega = true;
+    int mega_B = 0, mega_grid = 0, mega_n_ops = 0, mega_ops_cap = 0;
+    MegaPlan mega_plan;
+    std::vector<MegaOp> mega_ops_host;
+    MegaOp *mega_ops = nullptr;
+    unsigned *mega_bar = nullptr;
+    float *mega_am_vals = nullptr;
+    int *mega_am_idx = nullptr;
+    bool mega_prepare(int B);
     bool fused_decode(int rows) const;
     void *xt_buf = nullptr;   // bf16 split tiles feeding the tcgen05 GEMM
     size_t xt_elems = 0;
