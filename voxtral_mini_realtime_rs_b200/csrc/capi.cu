@@ -702,6 +702,21 @@ int32_t vox_session_debug_read(vox_session *sh, const char *what, float *out, si
         s->use_graph = true;
         if (n_floats) *n_floats = 0;
         return VOX_OK;
+    } else if (w == "mega_trace") {
+        // phase trace of the last persistent decode step (CTA 0): per op {start, staged, body done,
+        // barrier passed, first weights ready | KV walked, last stage consumed} in microseconds since the first stamp; ops 0..mega_n_ops-1
+        const size_t cnt = (size_t)s->mega_n_ops * 6;
+        if (n_floats) *n_floats = cnt;
+        if (out) {
+            VOX_CHECK(cap >= cnt, VOX_ECAPACITY, "debug_read capacity %zu < %zu", cap, cnt);
+            CUDA_OK(cudaStreamSynchronize(s->st));
+            std::vector<unsigned long long> t(cnt);
+            if (cnt) CUDA_OK(cudaMemcpy(t.data(), s->mega_trace, sizeof(unsigned long long) * cnt, cudaMemcpyDeviceToHost));
+            int khz = 0;
+            CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, s->m->device));
+            for (size_t i = 0; i < cnt; ++i) out[i] = (float)((double)(t[i] - t[0]) / ((double)khz * 1e-3));
+        }
+        return VOX_OK;
     } else if (w == "enc_out") { src = s->h_enc; n = rows * c.enc_dim; }
     else if (w == "audio_embeds") { src = s->audio; n = (size_t)s->cur_B * s->cur_S4 * c.dec_dim; }
     else if (w == "mel") { src = s->mel; n = 0; /* size unknown here */ }

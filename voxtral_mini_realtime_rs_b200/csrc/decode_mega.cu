@@ -49,15 +49,20 @@ constexpr int MG_CWARPS = 16;                    // consumer warps
 constexpr int MG_CTHREADS = MG_CWARPS * 32;
 constexpr int MG_THREADS = MG_CTHREADS + 32;     // + the producer warp
 constexpr int MG_CHUNK = 16;                     // block pairs per ring stage (one per consumer warp)
-constexpr int MG_STAGE_Q = MG_CHUNK * 512;       // nibble bytes of a stage; scales follow
-constexpr int MG_STAGE_BYTES = MG_CHUNK * 576;
+constexpr int MG_SLOT_Q = MG_CHUNK * 512;        // nibble bytes of one tile's part of a stage; its scales follow
+constexpr int MG_SLOT_BYTES = MG_CHUNK * 576;    // a stage holds NT such slots (NT tiles advance together)
 constexpr int MG_MAX_STAGES = 24;
 constexpr int MG_ACC_TILES = 4;                  // tiles per CTA whose sums may persist across K slices
 constexpr int MG_SMEM_MAX = 227 * 1024;
 constexpr int MG_SCRATCH_CAP = 104448;           // 48 pairs at 8 tokens
 constexpr long long MG_SPIN_CYCLES = 4000000000ll;  // ~2 s: watchdog
 
-__host__ __device__ constexpr int mg_misc_bytes(int MT) { return ((416 + 2304 * MT) + 127) & ~127; }
+// tiles a CTA advances together (independent accumulation chains per warp, shared activation fragments)
+__host__ __device__ constexpr int mg_nt(int MT) { return MT <= 2 ? 4 : 2; }
+// barriers + rinv + red[2][16 warps][NT*16*MT] + acc_tile[MG_ACC_TILES][16*MT]
+__host__ __device__ constexpr int mg_misc_bytes(int MT) {
+    return ((432 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT) + 127) & ~127;
+}
 __host__ __device__ constexpr int mg_pair_bytes(int MT) { return 272 * MT; }  // fragments + offsets of one block pair
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,10 +107,35 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
+// L2 prefetch of a byte range (16-byte multiple)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
 }
 // barrier among the 512 consumer threads (the producer warp never joins)
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
@@ -125,16 +155,12 @@ __device__ __forceinline__ void amax_combine(float &bv, int &bx, const float ov,
     if (ov > bv || (ov == bv && ox < bx)) { bv = ov; bx = ox; }
 }
 
-__device__ __forceinline__ float4 eff4(const float4 v, const float rinv, const float *gamma, const float *ada, const int k) {
-    if (!gamma) return v;
-    const float4 g = *reinterpret_cast<const float4 *>(gamma + k);
-    float4 o = make_float4((v.x * rinv) * g.x, (v.y * rinv) * g.y, (v.z * rinv) * g.z, (v.w * rinv) * g.w);
-    if (ada) {
-        const float4 a = *reinterpret_cast<const float4 *>(ada + k);
-        o.x *= a.x; o.y *= a.y; o.z *= a.z; o.w *= a.w;
-    }
-    return o;
-}
+// Fused RMSNorm: `gamma` is the norm weight, for the FFN norm pre-multiplied by the session's ADA scale
+// (1 + w2.gelu(w0.t), constant per session; Session::set_delay).  The per-token factor 1/rms is a scalar
+// of the whole row, so it is applied to the finished dot product in the epilogue
+// (y = rinv * sum w*(x*gamma)) instead of to every activation: the staging pass then does not wait
+// for the row statistics.
+__device__ __forceinline__ float4 mul4(const float4 a, const float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 
 // Activation side of blocks [b0, b0+nb) -> shared memory (same encoding as matvec_tc.cu tc_stage):
 //   bf   : uint2  [nb][2 (nibble half)][2*MT cols][4 t]   B fragments of lane (g = col, t)
@@ -142,12 +168,12 @@ __device__ __forceinline__ float4 eff4(const float4 v, const float rinv, const f
 // Rows >= B (capacity padding) and blocks beyond K stage as zeros.
 template <int MT>
 __device__ __forceinline__ void mg_stage(const float *__restrict__ x, const int K, const int B, const float *gamma,
-                                         const float *ada, const int b0, const int nb, const float *__restrict__ rinv,
+                                         const int b0, const int nb,
                                          uint2 *__restrict__ bf, float2 *__restrict__ off2) {
     const int items = nb * MT * 4;
     constexpr int U = 2;
     for (int base = 0; base < items; base += MG_CTHREADS * U) {
-        float4 lo[U], hi[U];
+        float4 lo[U], hi[U], glo[U], ghi[U];
         int mm[U], bl[U];
         bool act[U], ld[U];
 #pragma unroll
@@ -160,9 +186,13 @@ __device__ __forceinline__ void mg_stage(const float *__restrict__ x, const int 
             lo[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             hi[u] = lo[u];
             ld[u] = act[u] && kb < K && mm[u] < B;
-            if (ld[u]) {
+            if (ld[u]) {  // all loads of the pass are in flight together (x from L2, norm vectors L1/L2)
                 lo[u] = __ldcg(reinterpret_cast<const float4 *>(x + (size_t)mm[u] * K + kb + 4 * t));
                 hi[u] = __ldcg(reinterpret_cast<const float4 *>(x + (size_t)mm[u] * K + kb + 16 + 4 * t));
+                if (gamma) {
+                    glo[u] = *reinterpret_cast<const float4 *>(gamma + kb + 4 * t);
+                    ghi[u] = *reinterpret_cast<const float4 *>(gamma + kb + 16 + 4 * t);
+                }
             }
         }
 #pragma unroll
@@ -171,9 +201,9 @@ __device__ __forceinline__ void mg_stage(const float *__restrict__ x, const int 
             const int t = i & 3, m = mm[u];
             const int kb = (b0 + bl[u]) * 32;
             float4 l = lo[u], h = hi[u];
-            if (ld[u]) {
-                l = eff4(l, rinv[m], gamma, ada, kb + 4 * t);
-                h = eff4(h, rinv[m], gamma, ada, kb + 16 + 4 * t);
+            if (ld[u] && gamma) {
+                l = mul4(l, glo[u]);
+                h = mul4(h, ghi[u]);
             }
             float bs = ((l.x + l.y) + (l.z + l.w)) + ((h.x + h.y) + (h.z + h.w));
             float bm = fmaxf(fmaxf(fmaxf(fabsf(l.x), fabsf(l.y)), fmaxf(fabsf(l.z), fabsf(l.w))),
@@ -217,13 +247,14 @@ template <int MT, int G, int DPL>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaParams p) {
     constexpr int CG = (MT + 3) / 4;
     constexpr int HD = DPL * 32;
-    constexpr int RW = (16 * MT + 31) / 32;  // warps that add the per-warp partial sums and run the epilogue
+    constexpr int NT = mg_nt(MT);
+    constexpr int RW = (NT * 16 * MT + 31) / 32;  // warps that add the per-warp partial sums and run the epilogue
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + MG_MAX_STAGES;
-    float *rinv = reinterpret_cast<float *>(empty + MG_MAX_STAGES);   // [8]
-    float *red = rinv + 8;                                            // [2][MG_CWARPS][16*MT]
-    float *acc_tile = red + 2 * MG_CWARPS * 16 * MT;                  // [MG_ACC_TILES][16*MT]
+    float *rinv = reinterpret_cast<float *>(empty + MG_MAX_STAGES + 2);  // [8]
+    float *red = rinv + 8;                                            // [2][MG_CWARPS][NT*16*MT]
+    float *acc_tile = red + 2 * MG_CWARPS * NT * 16 * MT;             // [MG_ACC_TILES][16*MT]
     unsigned char *scratch = smem + mg_misc_bytes(MT);
     unsigned char *ring = scratch + p.scratch_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -247,8 +278,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             int stage = 0;
             uint32_t phase = 0;
             bool wrapped = false;
+            // weights are read once per step: evict-first keeps the KV cache, the activations and the norm
+            // vectors resident in L2 under the 1.9 GB/step weight stream
+            const uint64_t pol = policy_evict_first();
+            const int flags = p.flags;
             for (int oi = 0; oi < p.n_ops; ++oi) {
                 const MegaOp &op = p.ops[oi];
+                // pull what the consumers touch first in the NEXT phase into L2 now
+                if (oi + 1 < p.n_ops) {
+                    const MegaOp &nx = p.ops[oi + 1];
+                    if (nx.kind == MG_MATVEC && (oi % nctas) == cta && !(flags & 4)) {
+                        if (nx.gamma) bulk_prefetch_l2(nx.gamma, (uint32_t)nx.K * 4u);
+                    }
+                }
                 if (op.kind != MG_MATVEC) continue;
                 const int n_tiles = op.n_tiles, n_pairs = op.n_pairs, S = op.S, Ps = op.Ps;
                 const uint4 *qs = op.qs_tc;
@@ -257,16 +299,23 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 for (int s = 0; s < S; ++s) {
                     const int pb = s * Ps;
                     const int np = min(Ps, n_pairs - pb);
-                    for (int it = 0; it < ntl; ++it) {
-                        const int tile = cta + it * nctas;
+                    for (int it = 0; it < ntl; it += NT) {
+                        const int nt = min(NT, ntl - it);
                         for (int c0 = 0; c0 < np; c0 += MG_CHUNK) {
                             const int nb = min(MG_CHUNK, np - c0);
                             if (wrapped) mbar_wait(&empty[stage], phase ^ 1u, wd_flag, 0x100u + (unsigned)oi);
-                            unsigned char *dst = ring + (size_t)stage * MG_STAGE_BYTES;
-                            mbar_expect_tx(&full[stage], (uint32_t)nb * 576u);
-                            const size_t pair0 = (size_t)tile * n_pairs + pb + c0;
-                            bulk_g2s(dst, qs + pair0 * 32, (uint32_t)nb * 512u, &full[stage]);
-                            bulk_g2s(dst + MG_STAGE_Q, ds + pair0 * 8, (uint32_t)nb * 64u, &full[stage]);
+                            unsigned char *dst = ring + (size_t)stage * (NT * MG_SLOT_BYTES);
+                            mbar_expect_tx(&full[stage], (uint32_t)(nt * nb) * 576u);
+                            for (int u = 0; u < nt; ++u) {
+                                const size_t pair0 = (size_t)(cta + (it + u) * nctas) * n_pairs + pb + c0;
+                                if (flags & 1) {
+                                    bulk_g2s(dst + (size_t)u * MG_SLOT_BYTES, qs + pair0 * 32, (uint32_t)nb * 512u, &full[stage]);
+                                    bulk_g2s(dst + (size_t)u * MG_SLOT_BYTES + MG_SLOT_Q, ds + pair0 * 8, (uint32_t)nb * 64u, &full[stage]);
+                                } else {
+                                    bulk_g2s_hint(dst + (size_t)u * MG_SLOT_BYTES, qs + pair0 * 32, (uint32_t)nb * 512u, &full[stage], pol);
+                                    bulk_g2s_hint(dst + (size_t)u * MG_SLOT_BYTES + MG_SLOT_Q, ds + pair0 * 8, (uint32_t)nb * 64u, &full[stage], pol);
+                                }
+                            }
                             if (++stage == nstage) {
                                 stage = 0;
                                 phase ^= 1u;
@@ -293,9 +342,22 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     for (int oi = 0; oi < p.n_ops; ++oi) {
         const MegaOp &op = p.ops[oi];
         const int kind = op.kind;
+        const bool tracing = p.trace != nullptr && cta == 0 && tid == 0;
+        if (tracing) {
+            const unsigned long long now = (unsigned long long)clock64();
+            p.trace[oi * 6 + 0] = now;
+            p.trace[oi * 6 + 1] = now;
+            p.trace[oi * 6 + 4] = now;
+            p.trace[oi * 6 + 5] = now;
+        }
+        if (tid == 0 && oi + 1 < p.n_ops) {  // next phase's descriptor -> L1 (off its critical path)
+            prefetch_l1(&p.ops[oi + 1]);
+            prefetch_l1(reinterpret_cast<const unsigned char *>(&p.ops[oi + 1]) + 128);
+        }
         if (kind == MG_MATVEC) {
             const int n_tiles = op.n_tiles, n_pairs = op.n_pairs, S = op.S, Ps = op.Ps, N = op.N, K = op.K;
             const int epi = op.epi, ldy = op.ldy, track = op.track_argmax;
+            const bool has_norm = op.gamma != nullptr;
             float *const yout = op.y;
             const float *const bias = op.bias, *const resid = op.res;
             float *const ssq_out = op.ssq_out;
@@ -306,56 +368,101 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 for (int s = 0; s < S; ++s) {
                     const int pb = s * Ps;
                     const int np = min(Ps, n_pairs - pb);
-                    if (s == 0 && op.gamma && warp < B) {
+                    // row statistics of the fused RMSNorm: the loads are issued before the staging pass and
+                    // consumed after it (the epilogue is their first user)
+                    const bool stats = (s == 0) && has_norm && warp < B;
+                    float pr[8];
+                    if (stats) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int i = lane + 32 * q;
+                            pr[q] = i < op.ssq_in_parts ? __ldcg(op.ssq_in + (size_t)i * B + warp) : 0.0f;
+                        }
+                    }
+                    cbar();  // every warp is done with the previous contents of scratch
+                    mg_stage<MT>(op.x, K, B, op.gamma, pb * 2, np * 2, bf, off2);
+                    if (stats) {
                         float ss = 0.0f;
-                        for (int i = lane; i < op.ssq_in_parts; i += 32) ss += __ldcg(op.ssq_in + (size_t)i * B + warp);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) ss += pr[q];
+                        for (int i = lane + 256; i < op.ssq_in_parts; i += 32) ss += __ldcg(op.ssq_in + (size_t)i * B + warp);
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
                         if (lane == 0) rinv[warp] = 1.0f / sqrtf(ss / (float)K + p.eps);
                     }
-                    cbar();  // rinv visible; every warp is done with the previous contents of scratch
-                    mg_stage<MT>(op.x, K, B, op.gamma, op.ada, pb * 2, np * 2, rinv, bf, off2);
                     cbar();
-                    for (int it = 0; it < ntl; ++it) {
-                        const int tile = cta + it * nctas;
-                        float acc[CG][2];
+                    if (tracing && s == 0) p.trace[oi * 6 + 1] = (unsigned long long)clock64();
+                    // the CTA's tiles (cta, cta+grid, ...) NT at a time: every warp carries NT independent
+                    // accumulation chains that share one read of the activation fragments
+                    for (int it = 0; it < ntl; it += NT) {
+                        const int nt = min(NT, ntl - it);
+                        float acc[NT][CG][2];
 #pragma unroll
-                        for (int c = 0; c < CG; ++c) acc[c][0] = acc[c][1] = 0.0f;
+                        for (int u = 0; u < NT; ++u)
+#pragma unroll
+                            for (int c = 0; c < CG; ++c) acc[u][c][0] = acc[u][c][1] = 0.0f;
+                        // reducer threads: (tile slot, token, row) = (tid / 16MT, (tid % 16MT) / 16, tid % 16)
+                        const int r_slot = tid / (16 * MT), r_tok = (tid % (16 * MT)) >> 4, r_r = tid & 15;
+                        const int r_tile = cta + (it + r_slot) * nctas;
+                        const int r_row = r_tile * 16 + r_r;
+                        const bool r_valid = tid < NT * 16 * MT && r_slot < nt;
+                        // the epilogue's residual operand: fetched now, used after the tile's weight stream
+                        float res_pre = 0.0f;
+                        if (epi == EPI_RESIDUAL && s + 1 == S && r_valid && r_tok < B && r_row < N)
+                            res_pre = __ldcg(resid + (size_t)r_tok * ldy + r_row);
                         for (int c0 = 0; c0 < np; c0 += MG_CHUNK) {
                             mbar_wait(&full[stage], phase, wd_flag, 0x200u + (unsigned)oi);
+                            if (tracing && s == 0 && it == 0 && c0 == 0) p.trace[oi * 6 + 4] = (unsigned long long)clock64();
                             const int pp = c0 + warp;  // pair index inside the slice
                             if (pp < np) {
-                                const unsigned char *sb = ring + (size_t)stage * MG_STAGE_BYTES;
-                                const uint4 wq = reinterpret_cast<const uint4 *>(sb)[warp * 32 + lane];
-                                const uint2 wd = reinterpret_cast<const uint2 *>(sb + MG_STAGE_Q)[warp * 8 + g];
-                                const uint32_t words[2][2] = {{wq.x, wq.y}, {wq.z, wq.w}};
-                                const __half2 dlo = *reinterpret_cast<const __half2 *>(&wd.x);
-                                const __half2 dhi = *reinterpret_cast<const __half2 *>(&wd.y);
-                                const float dsc[2][2] = {{__low2float(dlo), __high2float(dlo)},
-                                                         {__low2float(dhi), __high2float(dhi)}};
+                                const unsigned char *sb = ring + (size_t)stage * (NT * MG_SLOT_BYTES);
+                                uint4 wq[NT];
+                                uint2 wd[NT];
+#pragma unroll
+                                for (int u = 0; u < NT; ++u) {
+                                    if (u < nt) {
+                                        wq[u] = reinterpret_cast<const uint4 *>(sb + (size_t)u * MG_SLOT_BYTES)[warp * 32 + lane];
+                                        wd[u] = reinterpret_cast<const uint2 *>(sb + (size_t)u * MG_SLOT_BYTES + MG_SLOT_Q)[warp * 8 + g];
+                                    }
+                                }
 #pragma unroll
                                 for (int bb = 0; bb < 2; ++bb) {
                                     const int bl = pp * 2 + bb;
-                                    const uint32_t wg = words[bb][0], wg8 = words[bb][1];
-                                    const uint32_t sg = wg >> 8, sg8 = wg8 >> 8;
-                                    const uint32_t a_lo[4] = {wg & 0x000F000Fu, wg8 & 0x000F000Fu, sg & 0x000F000Fu, sg8 & 0x000F000Fu};
-                                    const uint32_t a_hi[4] = {wg & 0x00F000F0u, wg8 & 0x00F000F0u, sg & 0x00F000F0u, sg8 & 0x00F000F0u};
                                     const uint2 *bfb = bf + (size_t)(bl * 2) * (2 * MT) * 4;
+                                    uint2 blo[CG], bhi[CG];
+                                    float2 of[CG];
 #pragma unroll
                                     for (int c = 0; c < CG; ++c) {
                                         const int col = c * 8 + g;
-                                        uint2 blo = make_uint2(0u, 0u), bhi = blo;
+                                        blo[c] = make_uint2(0u, 0u);
+                                        bhi[c] = blo[c];
                                         if (col < 2 * MT) {
-                                            blo = bfb[col * 4 + t];
-                                            bhi = bfb[(2 * MT + col) * 4 + t];
+                                            blo[c] = bfb[col * 4 + t];
+                                            bhi[c] = bfb[(2 * MT + col) * 4 + t];
                                         }
-                                        float cc[4] = {0.f, 0.f, 0.f, 0.f};
-                                        mma16816(cc, a_lo[0], a_lo[1], a_lo[2], a_lo[3], blo.x, blo.y);
-                                        mma16816(cc, a_hi[0], a_hi[1], a_hi[2], a_hi[3], bhi.x, bhi.y);
                                         const int tok = c * 4 + t;
-                                        const float2 o = tok < MT ? off2[bl * MT + tok] : make_float2(0.0f, 0.0f);
-                                        acc[c][0] = fmaf(dsc[bb][0], fmaf(cc[0] + cc[1], o.y, o.x), acc[c][0]);
-                                        acc[c][1] = fmaf(dsc[bb][1], fmaf(cc[2] + cc[3], o.y, o.x), acc[c][1]);
+                                        of[c] = tok < MT ? off2[bl * MT + tok] : make_float2(0.0f, 0.0f);
+                                    }
+#pragma unroll
+                                    for (int u = 0; u < NT; ++u) {
+                                        if (u < nt) {
+                                            const uint32_t wg = bb ? wq[u].z : wq[u].x, wg8 = bb ? wq[u].w : wq[u].y;
+                                            const uint32_t dw = bb ? wd[u].y : wd[u].x;
+                                            const __half2 dh = *reinterpret_cast<const __half2 *>(&dw);
+                                            const float d0 = __low2float(dh), d1 = __high2float(dh);
+                                            const uint32_t sg = wg >> 8, sg8 = wg8 >> 8;
+                                            const uint32_t a_lo[4] = {wg & 0x000F000Fu, wg8 & 0x000F000Fu, sg & 0x000F000Fu, sg8 & 0x000F000Fu};
+                                            const uint32_t a_hi[4] = {wg & 0x00F000F0u, wg8 & 0x00F000F0u, sg & 0x00F000F0u, sg8 & 0x00F000F0u};
+#pragma unroll
+                                            for (int c = 0; c < CG; ++c) {
+                                                // two independent MMAs (low / high nibbles), summed afterwards
+                                                float cl[4] = {0.f, 0.f, 0.f, 0.f}, ch[4] = {0.f, 0.f, 0.f, 0.f};
+                                                mma16816(cl, a_lo[0], a_lo[1], a_lo[2], a_lo[3], blo[c].x, blo[c].y);
+                                                mma16816(ch, a_hi[0], a_hi[1], a_hi[2], a_hi[3], bhi[c].x, bhi[c].y);
+                                                acc[u][c][0] = fmaf(d0, fmaf((cl[0] + ch[0]) + (cl[1] + ch[1]), of[c].y, of[c].x), acc[u][c][0]);
+                                                acc[u][c][1] = fmaf(d1, fmaf((cl[2] + ch[2]) + (cl[3] + ch[3]), of[c].y, of[c].x), acc[u][c][1]);
+                                            }
+                                        }
                                     }
                                 }
                             }
@@ -366,47 +473,50 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                                 phase ^= 1u;
                             }
                         }
-                        // ---- the 16 warps' partial sums of this tile meet in shared memory
-                        float *rw = red + (size_t)(par * MG_CWARPS + warp) * 16 * MT;
+                        if (tracing && s + 1 == S && it + NT >= ntl) p.trace[oi * 6 + 5] = (unsigned long long)clock64();
+                        // ---- the 16 warps' partial sums of these tiles meet in shared memory
+                        float *rw = red + (size_t)(par * MG_CWARPS + warp) * (NT * 16 * MT);
 #pragma unroll
-                        for (int c = 0; c < CG; ++c) {
-                            const int tok = c * 4 + t;
-                            if (tok < MT) {
-                                rw[tok * 16 + g] = acc[c][0];
-                                rw[tok * 16 + g + 8] = acc[c][1];
+                        for (int u = 0; u < NT; ++u) {
+                            if (u < nt) {
+#pragma unroll
+                                for (int c = 0; c < CG; ++c) {
+                                    const int tok = c * 4 + t;
+                                    if (tok < MT) {
+                                        rw[(u * MT + tok) * 16 + g] = acc[u][c][0];
+                                        rw[(u * MT + tok) * 16 + g + 8] = acc[u][c][1];
+                                    }
+                                }
                             }
                         }
                         cbar();
                         if (warp < RW) {
-                            const int i = tid;
-                            const bool valid = i < 16 * MT;
-                            const int tok = i >> 4, r = i & 15;
-                            const int row = tile * 16 + r;
                             float v = 0.0f;
-                            if (valid) {
-                                const float *rp = red + (size_t)par * MG_CWARPS * 16 * MT + i;
+                            if (r_valid) {
+                                const float *rp = red + (size_t)par * MG_CWARPS * (NT * 16 * MT) + tid;
 #pragma unroll
-                                for (int w = 0; w < MG_CWARPS; ++w) v += rp[w * 16 * MT];
+                                for (int w = 0; w < MG_CWARPS; ++w) v += rp[w * (NT * 16 * MT)];
                                 if (S > 1) {
-                                    float *at = acc_tile + (size_t)it * 16 * MT + i;
+                                    float *at = acc_tile + (size_t)(it + r_slot) * 16 * MT + (tid % (16 * MT));
                                     if (s > 0) v += *at;
                                     if (s + 1 < S) *at = v;
                                 }
                             }
                             if (s + 1 == S) {
-                                const bool live = valid && tok < B;
+                                const bool live = r_valid && r_tok < B;
+                                if (has_norm && live) v *= rinv[r_tok];
                                 if (epi == EPI_SILU_MUL) {
                                     const float o = __shfl_xor_sync(0xffffffffu, v, 1);
-                                    if (live && !(r & 1) && row + 1 < N)
-                                        yout[(size_t)tok * ldy + (row >> 1)] = (v / (1.0f + expf(-v))) * o;
+                                    if (live && !(r_r & 1) && r_row + 1 < N)
+                                        yout[(size_t)r_tok * ldy + (r_row >> 1)] = (v / (1.0f + expf(-v))) * o;
                                 } else {
                                     float out = 0.0f;
-                                    if (live && row < N) {
-                                        out = v + (bias ? bias[row] : 0.0f);
-                                        if (epi == EPI_RESIDUAL) out += __ldcg(resid + (size_t)tok * ldy + row);
+                                    if (live && r_row < N) {
+                                        out = v + (bias ? bias[r_row] : 0.0f);
+                                        if (epi == EPI_RESIDUAL) out += res_pre;
                                         if (epi == EPI_GELU) out = 0.5f * out * (1.0f + erff(out * 0.70710678118654752440f));
-                                        yout[(size_t)tok * ldy + row] = out;
-                                        if (track) amax_combine(best_v, best_i, out, row);
+                                        yout[(size_t)r_tok * ldy + r_row] = out;
+                                        if (track) amax_combine(best_v, best_i, out, r_row);
                                     }
                                     if (ssq_out) {
                                         float sq = out * out;
@@ -414,7 +524,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                                         sq += __shfl_xor_sync(0xffffffffu, sq, 4);
                                         sq += __shfl_xor_sync(0xffffffffu, sq, 2);
                                         sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                                        if (live && r == 0) ssq_out[(size_t)tile * B + tok] = sq;
+                                        if (live && r_r == 0) ssq_out[(size_t)r_tile * B + r_tok] = sq;
                                     }
                                 }
                             }
@@ -424,53 +534,76 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 }
             }
             if (track && warp < RW) {
-                // this CTA's best candidate per stream (lowest index wins ties: order independent)
+                // this CTA's best candidate per stream (lowest index wins ties: order independent):
+                // first the 16 rows of a (slot, token) group, then the NT slots through shared memory
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) {
                     const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
                     const int ox = __shfl_xor_sync(0xffffffffu, best_i, o);
                     amax_combine(best_v, best_i, ov, ox);
                 }
-                const int tok = tid >> 4;
-                if ((tid & 15) == 0 && tok < B) {
-                    p.am_vals[(size_t)cta * 8 + tok] = best_v;
-                    p.am_idx[(size_t)cta * 8 + tok] = best_i;
+                float *cv = red;  // red is idle between ops: [NT][MT] values, then [NT][MT] indices
+                int *ci = reinterpret_cast<int *>(red + NT * MT);
+                if ((tid & 15) == 0 && tid < NT * 16 * MT) {
+                    cv[tid >> 4] = best_v;
+                    ci[tid >> 4] = best_i;
                 }
                 best_v = -INFINITY;
                 best_i = 0x7fffffff;
             }
+            if (track) {
+                cbar();
+                if (tid < B) {
+                    float bv = -INFINITY;
+                    int bx = 0x7fffffff;
+                    const float *cv = red;
+                    const int *ci = reinterpret_cast<const int *>(red + NT * MT);
+#pragma unroll
+                    for (int u = 0; u < NT; ++u) amax_combine(bv, bx, cv[u * MT + tid], ci[u * MT + tid]);
+                    p.am_vals[(size_t)cta * 8 + tid] = bv;
+                    p.am_idx[(size_t)cta * 8 + tid] = bx;
+                }
+            }
         } else if (kind == MG_ATTN) {
+            // unit = (stream, kv head, key chunk): the 4 query heads of a GQA group share one pass over their
+            // chunk of K and V; the chunks' softmax states are combined in the MG_ATTN_MERGE phase.  (One CTA
+            // per (stream, kv head) walked all keys in ~17 us -- issue-bound -- while 140 SMs waited.)
             float *qs = reinterpret_cast<float *>(scratch);       // [G][HD]
             float *kvs = qs + G * HD;                              // [2][HD]
             float *red_m = kvs + 2 * HD;                           // [MG_CWARPS][G]
             float *red_l = red_m + MG_CWARPS * G;                  // [MG_CWARPS][G]
             float *red_acc = red_l + MG_CWARPS * G;                // [MG_CWARPS][G][HD]
-            const int H = p.H, Hkv = p.Hkv, max_seq = p.max_seq;
-            for (int unit = cta; unit < B * Hkv && pos < max_seq; unit += nctas) {
-                const int b = unit / Hkv, kvh = unit - b * Hkv;
+            const int H = p.H, Hkv = p.Hkv, max_seq = p.max_seq, NC = p.attn_chunks;
+            const int j_lo = pos - p.window > 0 ? pos - p.window : 0;
+            const int per = (pos - j_lo + NC) / NC;  // ceil((pos - j_lo + 1) / NC) keys per chunk
+            for (int unit = cta; unit < B * Hkv * NC && pos < max_seq; unit += nctas) {
+                const int ch = unit % NC, bk = unit / NC;
+                const int b = bk / Hkv, kvh = bk - b * Hkv;
+                const int j0 = j_lo + ch * per, j1 = min(pos + 1, j0 + per);  // keys [j0, j1)
+                const bool has_new = j0 <= pos && pos < j1;                    // this chunk holds the new row
                 const float *row = p.qkv + (size_t)b * p.ld_qkv;
                 cbar();  // scratch free (previous unit / previous op)
-                for (int i = tid; i < G * HD; i += MG_CTHREADS) qs[i] = __ldcg(row + (size_t)(kvh * G) * HD + i);
-                for (int i = tid; i < HD; i += MG_CTHREADS) {
-                    kvs[i] = __ldcg(row + (size_t)H * HD + kvh * HD + i);
-                    kvs[HD + i] = __ldcg(row + (size_t)(H + Hkv) * HD + kvh * HD + i);
-                }
-                cbar();
+                // q (G heads) and k through RoPE on the way in (rope.rs:103-141: interleaved pairs), v as is
                 constexpr int half = HD / 2;
                 for (int i = tid; i < (G + 1) * half; i += MG_CTHREADS) {
                     const int h = i / half, pi = i - h * half;
-                    float *v = (h < G) ? &qs[h * HD + 2 * pi] : &kvs[2 * pi];
+                    const float *src = (h < G) ? row + (size_t)(kvh * G + h) * HD + 2 * pi : row + (size_t)H * HD + kvh * HD + 2 * pi;
+                    const float2 xv = __ldcg(reinterpret_cast<const float2 *>(src));
                     const float c = p.cos_t[(size_t)pos * half + pi], sn = p.sin_t[(size_t)pos * half + pi];
-                    const float xr = v[0], xi = v[1];
-                    v[0] = xr * c - xi * sn;
-                    v[1] = xr * sn + xi * c;
+                    float *dst = (h < G) ? &qs[h * HD + 2 * pi] : &kvs[2 * pi];
+                    dst[0] = xv.x * c - xv.y * sn;
+                    dst[1] = xv.x * sn + xv.y * c;
                 }
+                for (int i = tid; i < HD; i += MG_CTHREADS) kvs[HD + i] = __ldcg(row + (size_t)(H + Hkv) * HD + kvh * HD + i);
                 cbar();
+                if (tracing) p.trace[oi * 6 + 1] = (unsigned long long)clock64();
                 float *kbase = op.kc + ((size_t)b * Hkv + kvh) * max_seq * HD;
                 float *vbase = op.vc + ((size_t)b * Hkv + kvh) * max_seq * HD;
-                for (int i = tid; i < HD; i += MG_CTHREADS) {
-                    kbase[(size_t)pos * HD + i] = kvs[i];
-                    vbase[(size_t)pos * HD + i] = kvs[HD + i];
+                if (has_new) {
+                    for (int i = tid; i < HD; i += MG_CTHREADS) {
+                        kbase[(size_t)pos * HD + i] = kvs[i];
+                        vbase[(size_t)pos * HD + i] = kvs[HD + i];
+                    }
                 }
                 float q[G][DPL];
 #pragma unroll
@@ -485,48 +618,78 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
 #pragma unroll
                     for (int i = 0; i < DPL; ++i) acc[h][i] = 0.0f;
                 }
-                const int j_lo = pos - p.window > 0 ? pos - p.window : 0;
-                for (int j = j_lo + warp; j <= pos; j += MG_CWARPS) {
-                    float kk[DPL], vv[DPL];
-                    if (j == pos) {  // the row appended above: take it from shared memory
+                constexpr int KU = 4;  // keys in flight per warp; one softmax rescale per KU keys
+                for (int jb = j0 + warp; jb < j1; jb += KU * MG_CWARPS) {
+                    float kk[KU][DPL], vv[KU][DPL];
 #pragma unroll
-                        for (int i = 0; i < DPL; ++i) {
-                            kk[i] = kvs[lane * DPL + i];
-                            vv[i] = kvs[HD + lane * DPL + i];
-                        }
-                    } else {
-                        const float *kr = kbase + (size_t)j * HD + lane * DPL;
-                        const float *vr = vbase + (size_t)j * HD + lane * DPL;
+                    for (int u = 0; u < KU; ++u) {
+                        const int j = jb + u * MG_CWARPS;
+                        if (j < j1 && j != pos) {
+                            const float *kr = kbase + (size_t)j * HD + lane * DPL;
+                            const float *vr = vbase + (size_t)j * HD + lane * DPL;
+                            if constexpr (DPL == 4) {
+                                const float4 k4 = *reinterpret_cast<const float4 *>(kr);
+                                const float4 v4 = *reinterpret_cast<const float4 *>(vr);
+                                kk[u][0] = k4.x; kk[u][1] = k4.y; kk[u][2] = k4.z; kk[u][3] = k4.w;
+                                vv[u][0] = v4.x; vv[u][1] = v4.y; vv[u][2] = v4.z; vv[u][3] = v4.w;
+                            } else {
 #pragma unroll
-                        for (int i = 0; i < DPL; ++i) {
-                            kk[i] = kr[i];
-                            vv[i] = vr[i];
+                                for (int i = 0; i < DPL; ++i) {
+                                    kk[u][i] = kr[i];
+                                    vv[u][i] = vr[i];
+                                }
+                            }
+                        } else {  // j == pos: the row appended above, still in shared memory (j >= j1: unused)
+#pragma unroll
+                            for (int i = 0; i < DPL; ++i) {
+                                kk[u][i] = kvs[lane * DPL + i];
+                                vv[u][i] = kvs[HD + lane * DPL + i];
+                            }
                         }
                     }
-                    float sc[G];
+                    float sc[KU][G];
 #pragma unroll
-                    for (int h = 0; h < G; ++h) {
-                        float d = 0.0f;
+                    for (int u = 0; u < KU; ++u)
 #pragma unroll
-                        for (int i = 0; i < DPL; ++i) d = fmaf(q[h][i], kk[i], d);
-                        sc[h] = d;
-                    }
+                        for (int h = 0; h < G; ++h) {
+                            float d = 0.0f;
+#pragma unroll
+                            for (int i = 0; i < DPL; ++i) d = fmaf(q[h][i], kk[u][i], d);
+                            sc[u][h] = d;
+                        }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                        for (int h = 0; h < G; ++h) sc[h] += __shfl_xor_sync(0xffffffffu, sc[h], o);
+                        for (int u = 0; u < KU; ++u)
+#pragma unroll
+                            for (int h = 0; h < G; ++h) sc[u][h] += __shfl_xor_sync(0xffffffffu, sc[u][h], o);
 #pragma unroll
                     for (int h = 0; h < G; ++h) {
-                        const float s1 = sc[h] * p.scale;
-                        const float m_new = fmaxf(m_run[h], s1);
-                        const float alpha = expf(m_run[h] - m_new);
-                        const float pe = expf(s1 - m_new);
-                        l_run[h] = l_run[h] * alpha + pe;
+                        float m_new = m_run[h];
+#pragma unroll
+                        for (int u = 0; u < KU; ++u) {
+                            sc[u][h] = (jb + u * MG_CWARPS < j1) ? sc[u][h] * p.scale : -INFINITY;
+                            m_new = fmaxf(m_new, sc[u][h]);
+                        }
+                        const float alpha = expf(m_run[h] - m_new);  // exp(-inf) = 0 on the first batch
+                        float pe[KU], ps = 0.0f;
+#pragma unroll
+                        for (int u = 0; u < KU; ++u) {
+                            pe[u] = expf(sc[u][h] - m_new);  // masked keys: exp(-inf) = 0
+                            ps += pe[u];
+                        }
+                        l_run[h] = l_run[h] * alpha + ps;
                         m_run[h] = m_new;
 #pragma unroll
-                        for (int i = 0; i < DPL; ++i) acc[h][i] = fmaf(pe, vv[i], acc[h][i] * alpha);
+                        for (int i = 0; i < DPL; ++i) {
+                            float a = acc[h][i] * alpha;
+#pragma unroll
+                            for (int u = 0; u < KU; ++u) a = fmaf(pe[u], vv[u][i], a);
+                            acc[h][i] = a;
+                        }
                     }
                 }
+                if (tracing) p.trace[oi * 6 + 4] = (unsigned long long)clock64();
 #pragma unroll
                 for (int h = 0; h < G; ++h) {
                     if (lane == 0) {
@@ -537,6 +700,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                     for (int i = 0; i < DPL; ++i) red_acc[((size_t)warp * G + h) * HD + lane * DPL + i] = acc[h][i];
                 }
                 cbar();
+                // the unit's softmax state (max, sum, unnormalised weighted V) for the merge phase
                 for (int i = tid; i < G * HD; i += MG_CTHREADS) {
                     const int h = i / HD, d = i - h * HD;
                     float mx = -INFINITY;
@@ -550,8 +714,42 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         num = fmaf(red_acc[((size_t)w * G + h) * HD + d], f, num);
                         den = fmaf(red_l[w * G + h], f, den);
                     }
-                    p.attn_out[(size_t)b * (H * HD) + (size_t)(kvh * G + h) * HD + d] = num / den;
+                    p.att_acc[((size_t)unit * G + h) * HD + d] = num;
+                    if (d == 0) {
+                        p.att_ml[((size_t)unit * G + h) * 2 + 0] = mx;
+                        p.att_ml[((size_t)unit * G + h) * 2 + 1] = den;
+                    }
                 }
+            }
+        } else if (kind == MG_ATTN_MERGE) {
+            // attn[b][head][d] = sum_c acc_c e^(m_c - M) / sum_c l_c e^(m_c - M) over the key chunks, in chunk order
+            const int H = p.H, Hkv = p.Hkv, NC = p.attn_chunks;
+            const int total = B * H * HD;
+            for (int e = cta * MG_CTHREADS + tid; e < total && pos < p.max_seq; e += nctas * MG_CTHREADS) {
+                const int d = e % HD, hh = (e / HD) % H, b = e / (HD * H);
+                const int kvh = hh / G, h = hh - kvh * G;
+                const size_t u0 = ((size_t)b * Hkv + kvh) * NC;
+                float mc[16], lc[16], ac[16];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c < NC) {
+                        mc[c] = __ldcg(p.att_ml + ((u0 + c) * G + h) * 2 + 0);
+                        lc[c] = __ldcg(p.att_ml + ((u0 + c) * G + h) * 2 + 1);
+                        ac[c] = __ldcg(p.att_acc + ((u0 + c) * G + h) * HD + d);
+                        mx = fmaxf(mx, mc[c]);
+                    }
+                }
+                float num = 0.0f, den = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c < NC) {
+                        const float f = (mc[c] == -INFINITY) ? 0.0f : expf(mc[c] - mx);
+                        num = fmaf(ac[c], f, num);
+                        den = fmaf(lc[c], f, den);
+                    }
+                }
+                p.attn_out[e] = num / den;
             }
         } else if (kind == MG_EMBED) {
             // x_dec[b] = audio[b][pos] + dequant(E[tok[b]])   (model.rs:584-618, 938-946)
@@ -614,21 +812,25 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 }
             }
         }
+        if (tracing) p.trace[oi * 6 + 2] = (unsigned long long)clock64();
         // ---- grid barrier between phases
         if (oi + 1 < p.n_ops) {
             cbar();
             if (tid == 0) {
-                __threadfence();
-                atomicAdd(&p.bar[0], 1u);
+                // release: ordered after every consumer thread's stores by the barrier above (cumulativity);
+                // acquire: the spin load; the barrier below extends it to the CTA
+                red_release_add(&p.bar[0], 1u);
                 bar_target += (unsigned)nctas;
                 const long long t0 = clock64();
                 unsigned n = 0;
-                while (ld_acquire_u32(&p.bar[0]) < bar_target) {
+                // relaxed polls (an acquire load would invalidate L1 on every iteration), one acquire fence at the end
+                while (ld_relaxed_u32(&p.bar[0]) < bar_target) {
                     if ((++n & 0x3FFu) == 0 && clock64() - t0 > MG_SPIN_CYCLES) mg_die(wd_flag, 0x300u + (unsigned)oi);
                 }
-                __threadfence();
+                asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
             }
             cbar();
+            if (tracing) p.trace[oi * 6 + 3] = (unsigned long long)clock64();
         }
     }
     // the last CTA to finish re-arms the barrier for the next launch
@@ -686,10 +888,11 @@ MegaPlan decode_mega_plan(int B, int max_pairs, int H, int Hkv, int hd) {
     if (scratch < attn_bytes) scratch = attn_bytes;
     pl.scratch_bytes = (scratch + 127) & ~127;
     const int left = MG_SMEM_MAX - mg_misc_bytes(pl.MT) - pl.scratch_bytes;
-    int ns = left / MG_STAGE_BYTES;
+    const int stage_bytes = mg_nt(pl.MT) * MG_SLOT_BYTES;
+    int ns = left / stage_bytes;
     pl.nstage = ns > MG_MAX_STAGES ? MG_MAX_STAGES : ns;
     VOX_CHECK(pl.nstage >= 2, VOX_EINVAL, "decode_mega: no room for the weight ring (%d stages)", pl.nstage);
-    pl.smem_bytes = (size_t)mg_misc_bytes(pl.MT) + pl.scratch_bytes + (size_t)pl.nstage * MG_STAGE_BYTES;
+    pl.smem_bytes = (size_t)mg_misc_bytes(pl.MT) + pl.scratch_bytes + (size_t)pl.nstage * stage_bytes;
     return pl;
 }
 

@@ -13,6 +13,7 @@ enum MegaKind : int {
     MG_MATVEC = 1,  // y = epi(norm?(x) . W^T), weights streamed through the CTA's TMA ring
     MG_ATTN = 2,    // RoPE + KV append + GQA attention of one layer
     MG_ARGMAX = 3,  // combine the per-CTA lm_head candidates, write the token, advance the counters
+    MG_ATTN_MERGE = 4,  // combine the key chunks' softmax states of MG_ATTN into the attention output
 };
 
 // One grid-wide phase.  A grid barrier separates consecutive phases.
@@ -27,7 +28,7 @@ struct MegaOp {
     float *y = nullptr;
     int ldy = 0;
     const float *bias = nullptr, *res = nullptr;
-    const float *gamma = nullptr, *ada = nullptr;
+    const float *gamma = nullptr;   // fused RMSNorm weight (x ADA scale where the layer has one)
     const float *ssq_in = nullptr;  // [ssq_in_parts][B]
     int ssq_in_parts = 0;
     float *ssq_out = nullptr;       // [n_tiles][B]
@@ -47,6 +48,9 @@ struct MegaParams {
     float scale = 0.f;
     const float *cos_t = nullptr, *sin_t = nullptr;
     float *attn_out = nullptr;
+    int attn_chunks = 1;          // key chunks per (stream, kv head): spreads the KV walk over the grid
+    float *att_acc = nullptr;     // [B*Hkv*chunks][G][hd] unnormalised weighted V per chunk
+    float *att_ml = nullptr;      // [B*Hkv*chunks][G][2]  running max, sum of exp
     // embedding (row-major planes of the tied table)
     const uint4 *emb_qs = nullptr;
     const __half *emb_d = nullptr;
@@ -64,6 +68,11 @@ struct MegaParams {
     unsigned *bar = nullptr;
     // shared-memory plan
     int nstage = 0, scratch_bytes = 0;
+    // optional phase trace of CTA 0: 6 SM-clock stamps per op (start, staged, body done, barrier passed,
+    // first weights ready | KV walked, last weight stage consumed)
+    unsigned long long *trace = nullptr;
+    // experiment switches (VOX_MEGA_FLAGS): 1 no evict-first hint, 4 no gamma prefetch
+    int flags = 0;
 };
 
 struct MegaPlan {

@@ -964,6 +964,15 @@ void launch_reshape_rows(const float *src, float *dst, int B, int S, int S_out, 
     post_launch("reshape_rows");
 }
 
+__global__ void mul_vec_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] * b[i];
+}
+void launch_mul_vec(const float *a, const float *b, float *out, size_t n, cudaStream_t st) {
+    mul_vec_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, out, n);
+    post_launch("mul_vec");
+}
+
 __global__ void gelu_kernel(float *x, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] = gelu_erf(x[i]);

@@ -121,6 +121,8 @@ void launch_gather_last(const float *src, float *dst, int B, int M, int dim, cud
 // reshape_encoder_output is a pure view when S % factor == 0; otherwise rows are re-packed
 void launch_reshape_rows(const float *src, float *dst, int B, int S, int S_out, int dim, int factor,
                          cudaStream_t st);
+// out[i] = a[i] * b[i]
+void launch_mul_vec(const float *a, const float *b, float *out, size_t n, cudaStream_t st);
 // GELU in place
 void launch_gelu(float *x, size_t n, cudaStream_t st);
 

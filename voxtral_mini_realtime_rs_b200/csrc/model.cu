@@ -425,6 +425,7 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
         s->last_h = s->arena.alloc_n<float>(B * c.dec_dim);
         s->logits = s->arena.alloc_n<float>(B * c.vocab);
         s->ada = s->arena.alloc_n<float>((size_t)c.dec_layers * c.dec_dim);
+        s->ffn_gamma_ada = s->arena.alloc_n<float>((size_t)c.dec_layers * c.dec_dim);
         s->t_embed = s->arena.alloc_n<float>(c.dec_dim);
         s->ada_tmp = s->arena.alloc_n<float>(c.t_cond_dim);
         s->d_pos = s->arena.alloc_n<int>(1);
@@ -473,12 +474,17 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
             const char *mv = getenv("VOX_MEGA");
             s->use_mega = !(mv && mv[0] == '0');
             s->mega_grid = decode_mega_grid(m->device);
-            s->mega_ops_cap = 5 * c.dec_layers + 4;
+            s->mega_ops_cap = 6 * c.dec_layers + 4;
             s->mega_ops = s->arena.alloc_n<MegaOp>(s->mega_ops_cap);
             s->mega_bar = s->arena.alloc_n<unsigned>(4);
             CUDA_OK(cudaMemset(s->mega_bar, 0, sizeof(unsigned) * 4));
             s->mega_am_vals = s->arena.alloc_n<float>((size_t)s->mega_grid * 8);
             s->mega_am_idx = s->arena.alloc_n<int>((size_t)s->mega_grid * 8);
+            s->mega_att_units = std::max(s->mega_grid, 8 * c.dec_kv_heads) + 8 * c.dec_kv_heads;
+            s->mega_att_acc = s->arena.alloc_n<float>((size_t)s->mega_att_units * (c.dec_heads / c.dec_kv_heads) * c.dec_head_dim);
+            s->mega_att_ml = s->arena.alloc_n<float>((size_t)s->mega_att_units * (c.dec_heads / c.dec_kv_heads) * 2);
+            s->mega_trace = s->arena.alloc_n<unsigned long long>((size_t)s->mega_ops_cap * 6);
+            CUDA_OK(cudaMemset(s->mega_trace, 0, sizeof(unsigned long long) * s->mega_ops_cap * 6));
         }
         CUDA_OK(cudaMemset(s->d_pos, 0, sizeof(int)));
         CUDA_OK(cudaMemset(s->d_outpos, 0, sizeof(int)));
@@ -539,6 +545,7 @@ void Session::set_delay(float delay) {
         launch_q4_matvec(m->dec[j].ada0, t_embed, 1, ada_tmp, c.t_cond_dim, nullptr, nullptr, EPI_GELU, st);
         // dst = 1 + w2 . gelu(...)   (residual epilogue onto the vector of ones)
         launch_q4_matvec(m->dec[j].ada2, ada_tmp, 1, dst, c.dec_dim, nullptr, dst, EPI_RESIDUAL, st);
+        launch_mul_vec(m->dec[j].ffn_norm, dst, ffn_gamma_ada + (size_t)j * c.dec_dim, c.dec_dim, st);
     }
     CUDA_OK(cudaStreamSynchronize(st));
     delay_set = true;
@@ -681,7 +688,7 @@ bool Session::mega_prepare(int B) {
     std::vector<MegaOp> ops;
     bool ok = true;
     auto matvec = [&](const Q4Weight &w, const float *x, float *y, int ldy, const float *res, int epi, const float *gamma,
-                      const float *ada_v, bool ssq_out_, bool track) {
+                      bool ssq_out_, bool track) {
         MegaOp o;
         o.kind = MG_MATVEC;
         o.epi = epi;
@@ -703,7 +710,6 @@ bool Session::mega_prepare(int B) {
         o.ldy = ldy;
         o.res = res;
         o.gamma = gamma;
-        o.ada = ada_v;
         if (gamma) {
             o.ssq_in = ssq_x;
             o.ssq_in_parts = parts;
@@ -719,17 +725,20 @@ bool Session::mega_prepare(int B) {
     }
     for (int j = 0; j < c.dec_layers; ++j) {
         const DecLayerW &l = m->dec[j];
-        matvec(l.wqkv, x_dec, qkv_dec, qkvd, nullptr, EPI_NONE, l.attn_norm, nullptr, false, false);
+        matvec(l.wqkv, x_dec, qkv_dec, qkvd, nullptr, EPI_NONE, l.attn_norm, false, false);
         MegaOp a;
         a.kind = MG_ATTN;
         a.kc = kc + (size_t)j * layer_stride;
         a.vc = vc + (size_t)j * layer_stride;
         ops.push_back(a);
-        matvec(l.wo, attn_dec, x_dec, D, x_dec, EPI_RESIDUAL, nullptr, nullptr, true, false);
-        matvec(l.w13, x_dec, act_dec, c.dec_ffn, nullptr, EPI_SILU_MUL, l.ffn_norm, ada + (size_t)j * D, false, false);
-        matvec(l.w2, act_dec, x_dec, D, x_dec, EPI_RESIDUAL, nullptr, nullptr, true, false);
+        MegaOp am;
+        am.kind = MG_ATTN_MERGE;
+        ops.push_back(am);
+        matvec(l.wo, attn_dec, x_dec, D, x_dec, EPI_RESIDUAL, nullptr, true, false);
+        matvec(l.w13, x_dec, act_dec, c.dec_ffn, nullptr, EPI_SILU_MUL, ffn_gamma_ada + (size_t)j * D, false, false);
+        matvec(l.w2, act_dec, x_dec, D, x_dec, EPI_RESIDUAL, nullptr, true, false);
     }
-    matvec(m->tok_emb, x_dec, logits, c.vocab, nullptr, EPI_NONE, m->dec_norm, nullptr, false, true);
+    matvec(m->tok_emb, x_dec, logits, c.vocab, nullptr, EPI_NONE, m->dec_norm, false, true);
     {
         MegaOp f;
         f.kind = MG_ARGMAX;
@@ -766,6 +775,9 @@ void Session::decode_step(int B) {
         p.cos_t = m->dec_cos;
         p.sin_t = m->dec_sin;
         p.attn_out = attn_dec;
+        p.attn_chunks = std::max(1, std::min(16, std::min(mega_grid, mega_att_units - 8 * c.dec_kv_heads) / (B * c.dec_kv_heads)));
+        p.att_acc = mega_att_acc;
+        p.att_ml = mega_att_ml;
         p.emb_qs = m->tok_emb.qs;
         p.emb_d = m->tok_emb.d;
         p.D = c.dec_dim;
@@ -783,6 +795,11 @@ void Session::decode_step(int B) {
         p.bar = mega_bar;
         p.nstage = mega_plan.nstage;
         p.scratch_bytes = mega_plan.scratch_bytes;
+        p.trace = mega_trace;
+        {
+            static const int env_flags = getenv("VOX_MEGA_FLAGS") ? atoi(getenv("VOX_MEGA_FLAGS")) : 0;
+            p.flags = env_flags;
+        }
         launch_decode_mega(p, mega_plan, mega_grid, st);
         return;
     }

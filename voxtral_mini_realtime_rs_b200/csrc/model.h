@@ -102,6 +102,7 @@ struct Session {
     float *logits_all = nullptr;
     size_t logits_all_cap = 0;
     float *ada = nullptr, *t_embed = nullptr, *ada_tmp = nullptr;
+    float *ffn_gamma_ada = nullptr;  // [L][D] ffn_norm weight x ADA scale (persistent decode kernel)
     bool delay_set = false;
     int *d_pos = nullptr, *d_outpos = nullptr, *d_tok = nullptr, *d_ids = nullptr, *d_out = nullptr;
     int out_ld = 0;
@@ -130,6 +131,9 @@ struct Session {
     unsigned *mega_bar = nullptr;
     float *mega_am_vals = nullptr;
     int *mega_am_idx = nullptr;
+    float *mega_att_acc = nullptr, *mega_att_ml = nullptr;  // key-chunk softmax states (MG_ATTN -> MG_ATTN_MERGE)
+    int mega_att_units = 0;
+    unsigned long long *mega_trace = nullptr;  // [mega_ops_cap][6] SM-clock stamps of CTA 0 (debug "mega_trace")
     bool mega_prepare(int B);
     bool fused_decode(int rows) const;
     void *xt_buf = nullptr;   // bf16 split tiles feeding the tcgen05 GEMM
