@@ -28,6 +28,7 @@ def main():
     audio = np.stack([synth.speechlike(16.0, seed=1234 + i) for i in range(B)])
     model = vx.Q4ModelLoader.from_file(GGUF).load(0, max_batch=B, max_mel_frames=2400)
     tm = vx.Timings()
+    model.debug("mega_on")
     model.transcribe_pcm(audio, timings=tm)
     model.transcribe_pcm(audio, timings=tm)
     tr = model.debug("mega_trace")

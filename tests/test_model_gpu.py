@@ -77,6 +77,23 @@ def test_encoder_layers_capture(tiny_model, tiny_oracle):
     tiny_model.debug("capture_off")
 
 
+def test_encoder_attention_tensor_core_vs_simt(tiny_model, tiny_oracle):
+    """enc_attn_tc.cu (mma.sync, two-piece f16 operands; default) against the f32 SIMT kernel and the oracle:
+    same encoder output to f32 rounding noise, with the sliding window biting (window 20 < S)."""
+    _, mel = _mel(5.0, seed=77)
+    exp = tiny_oracle.encode_audio(mel)
+    tiny_model.debug("enc_attn_tc")
+    got_tc = tiny_model.encode_audio(mel).copy()
+    tiny_model.debug("enc_attn_simt")
+    try:
+        got_simt = tiny_model.encode_audio(mel).copy()
+    finally:
+        tiny_model.debug("enc_attn_tc")
+    assert np.abs(got_tc - exp).max() < 1e-3            # the north-star bound
+    assert np.abs(got_tc - got_simt).max() < 2e-5 * max(1.0, np.abs(got_simt).max())
+    assert np.abs(got_tc - exp).max() < 3 * np.abs(got_simt - exp).max() + 1e-6
+
+
 def test_sliding_window_bites(tiny_model, tiny_oracle):
     """tiny enc_window=20 < S: the window mask changes the result, and we match the oracle."""
     _, mel = _mel(3.0, seed=4)
@@ -133,7 +150,7 @@ def test_persistent_decode_kernel_matches_per_op_launches(vx, tiny_model8, tiny_
         n_ops = tiny_model8.launch_count() - n0
         lg_ops = tiny_model8.debug("logits").copy()
     finally:
-        tiny_model8.debug("mega_on")
+        tiny_model8.debug("mega_auto")
     for i in range(batch):
         assert got[i].tolist() == exp[i], i
     assert np.array_equal(got, ref)

@@ -684,12 +684,19 @@ int32_t vox_session_debug_read(vox_session *sh, const char *what, float *out, si
         if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
         if (n_floats) *n_floats = 0;
         return VOX_OK;
+    } else if (w == "enc_attn_simt" || w == "enc_attn_tc") {
+        s->use_enc_attn_tc = (w == "enc_attn_tc");
+        if (n_floats) *n_floats = 0;
+        return VOX_OK;
     } else if (w == "gemm_simt" || w == "gemm_tc") {
         s->use_gemm_tc = (w == "gemm_tc");
         if (n_floats) *n_floats = 0;
         return VOX_OK;
-    } else if (w == "mega_off" || w == "mega_on") {
-        s->use_mega = (w == "mega_on");
+    } else if (w == "mega_off" || w == "mega_on" || w == "mega_auto") {
+        // mega_on: persistent decode kernel for every batch size; mega_auto: default policy (B >= 2)
+        s->use_mega = (w != "mega_off");
+        s->mega_min_B = (w == "mega_on") ? 1 : 2;
+        s->mega_B = 0;
         if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
         if (n_floats) *n_floats = 0;
         return VOX_OK;

@@ -52,16 +52,18 @@ constexpr int MG_CHUNK = 16;                     // block pairs per ring stage (
 constexpr int MG_SLOT_Q = MG_CHUNK * 512;        // nibble bytes of one tile's part of a stage; its scales follow
 constexpr int MG_SLOT_BYTES = MG_CHUNK * 576;    // a stage holds NT such slots (NT tiles advance together)
 constexpr int MG_MAX_STAGES = 24;
-constexpr int MG_ACC_TILES = 4;                  // tiles per CTA whose sums may persist across K slices
+constexpr int MG_ACC_TILES = 2;                  // tiles per CTA whose sums may persist across K slices
 constexpr int MG_SMEM_MAX = 227 * 1024;
 constexpr int MG_SCRATCH_CAP = 104448;           // 48 pairs at 8 tokens
 constexpr long long MG_SPIN_CYCLES = 4000000000ll;  // ~2 s: watchdog
 
 // tiles a CTA advances together (independent accumulation chains per warp, shared activation fragments)
 __host__ __device__ constexpr int mg_nt(int MT) { return MT <= 2 ? 4 : 2; }
-// barriers + rinv + red[2][16 warps][NT*16*MT] + acc_tile[MG_ACC_TILES][16*MT]
+// epilogue outputs waiting to become fragments: up to two 32-value blocks x MT tokens per tile group
+__host__ __device__ constexpr int mg_vals(int MT) { return (MT <= 2 ? 2 : 1) * 32 * MT; }
+// barriers + rinv + red[2][16 warps][NT*16*MT] + acc_tile[MG_ACC_TILES][16*MT] + vals
 __host__ __device__ constexpr int mg_misc_bytes(int MT) {
-    return ((432 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT) + 127) & ~127;
+    return ((432 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT + 4 * mg_vals(MT)) + 127) & ~127;
 }
 __host__ __device__ constexpr int mg_pair_bytes(int MT) { return 272 * MT; }  // fragments + offsets of one block pair
 
@@ -137,6 +139,12 @@ __device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gm
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
         : "memory");
 }
+// barrier among the first NW warps (the epilogue warps of a matvec phase)
+template <int NW>
+__device__ __forceinline__ void rbar() {
+    if (NW == 1) __syncwarp();
+    else asm volatile("bar.sync 2, %0;\n" ::"n"(NW * 32) : "memory");
+}
 // barrier among the 512 consumer threads (the producer warp never joins)
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
 
@@ -151,6 +159,15 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+// The CTA's tile list of a matvec: units of UT consecutive tiles dealt round-robin to the CTAs
+// (UT = 1: plain interleaving).  n_tiles % UT == 0 (host-checked).
+__device__ __forceinline__ int mg_tile_count(const int n_tiles, const int UT, const int cta, const int nctas) {
+    const int n_units = n_tiles / UT;
+    return cta < n_units ? ((n_units - cta + nctas - 1) / nctas) * UT : 0;
+}
+__device__ __forceinline__ int mg_tile_of(const int i, const int UT, const int cta, const int nctas) {
+    return (cta + (i / UT) * nctas) * UT + (i % UT);
+}
 __device__ __forceinline__ void amax_combine(float &bv, int &bx, const float ov, const int ox) {
     if (ov > bv || (ov == bv && ox < bx)) { bv = ov; bx = ox; }
 }
@@ -162,85 +179,51 @@ __device__ __forceinline__ void amax_combine(float &bv, int &bx, const float ov,
 // for the row statistics.
 __device__ __forceinline__ float4 mul4(const float4 a, const float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 
-// Activation side of blocks [b0, b0+nb) -> shared memory (same encoding as matvec_tc.cu tc_stage):
-//   bf   : uint2  [nb][2 (nibble half)][2*MT cols][4 t]   B fragments of lane (g = col, t)
-//   off2 : float2 [nb][MT]   { -8 * sum_{k in block} x , 2^24 / block scale }
-// Rows >= B (capacity padding) and blocks beyond K stage as zeros.
+// Activation fragments of one 32-element block for one token (same encoding as matvec_tc.cu tc_stage):
+//   bf_blk  : uint2  [2 (nibble half j)][2*MT cols][4 t]   B fragments {b0,b1} of lane (g = col, t);
+//             column 2*m = f16 hi piece of token m, 2*m+1 = mid piece
+//   off_blk : float2 [MT]   { -8 * sum_{k in block} x , 2^24 / block scale }
+// One work item = (token m, t): elements 4t..4t+3 (l) and 16+4t..16+4t+3 (h) of the block, already
+// multiplied by the consumer's norm weight.  The four t-items of a block must sit in four adjacent
+// lanes (t = lane & 3) and all 32 lanes must call (inactive ones with act = false): block sum and
+// block max are 2-step shuffles.
 template <int MT>
-__device__ __forceinline__ void mg_stage(const float *__restrict__ x, const int K, const int B, const float *gamma,
-                                         const int b0, const int nb,
-                                         uint2 *__restrict__ bf, float2 *__restrict__ off2) {
-    const int items = nb * MT * 4;
-    constexpr int U = 2;
-    for (int base = 0; base < items; base += MG_CTHREADS * U) {
-        float4 lo[U], hi[U], glo[U], ghi[U];
-        int mm[U], bl[U];
-        bool act[U], ld[U];
+__device__ __forceinline__ void frag_build(const float4 l, const float4 h, const bool act, const int t, const int m,
+                                           uint2 *__restrict__ bf_blk, float2 *__restrict__ off_blk) {
+    float bs = ((l.x + l.y) + (l.z + l.w)) + ((h.x + h.y) + (h.z + h.w));
+    float bm = fmaxf(fmaxf(fmaxf(fabsf(l.x), fabsf(l.y)), fmaxf(fabsf(l.z), fabsf(l.w))),
+                     fmaxf(fmaxf(fabsf(h.x), fabsf(h.y)), fmaxf(fabsf(h.z), fabsf(h.w))));
+    bs += __shfl_xor_sync(0xffffffffu, bs, 1);
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+    bs += __shfl_xor_sync(0xffffffffu, bs, 2);
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+    if (!act) return;
+    int e = (int)((__float_as_uint(bm) >> 23) & 0xFF) - 127;
+    if (!(bm > 0.0f) || bm > 3.0e38f) e = 7;  // all-zero (or non-finite) block: scale 1
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    const float s = __uint_as_float((uint32_t)(7 - e + 127) << 23);     // block max -> [2^7, 2^8)
+    const float inv = __uint_as_float((uint32_t)(17 + e + 127) << 23);  // 2^24 / s
+    const float ev[8] = {l.x * s, l.y * s, l.z * s, l.w * s,
+                         h.x * s * 0.0625f, h.y * s * 0.0625f, h.z * s * 0.0625f, h.w * s * 0.0625f};
+    float hh[8], md[8];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = base + u * MG_CTHREADS + (int)threadIdx.x;
-            act[u] = i < items;
-            mm[u] = act[u] ? (i >> 2) % MT : 0;
-            bl[u] = act[u] ? (i >> 2) / MT : 0;
-            const int kb = (b0 + bl[u]) * 32, t = i & 3;
-            lo[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            hi[u] = lo[u];
-            ld[u] = act[u] && kb < K && mm[u] < B;
-            if (ld[u]) {  // all loads of the pass are in flight together (x from L2, norm vectors L1/L2)
-                lo[u] = __ldcg(reinterpret_cast<const float4 *>(x + (size_t)mm[u] * K + kb + 4 * t));
-                hi[u] = __ldcg(reinterpret_cast<const float4 *>(x + (size_t)mm[u] * K + kb + 16 + 4 * t));
-                if (gamma) {
-                    glo[u] = *reinterpret_cast<const float4 *>(gamma + kb + 4 * t);
-                    ghi[u] = *reinterpret_cast<const float4 *>(gamma + kb + 16 + 4 * t);
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = base + u * MG_CTHREADS + (int)threadIdx.x;
-            const int t = i & 3, m = mm[u];
-            const int kb = (b0 + bl[u]) * 32;
-            float4 l = lo[u], h = hi[u];
-            if (ld[u] && gamma) {
-                l = mul4(l, glo[u]);
-                h = mul4(h, ghi[u]);
-            }
-            float bs = ((l.x + l.y) + (l.z + l.w)) + ((h.x + h.y) + (h.z + h.w));
-            float bm = fmaxf(fmaxf(fmaxf(fabsf(l.x), fabsf(l.y)), fmaxf(fabsf(l.z), fabsf(l.w))),
-                             fmaxf(fmaxf(fabsf(h.x), fabsf(h.y)), fmaxf(fabsf(h.z), fabsf(h.w))));
-            bs += __shfl_xor_sync(0xffffffffu, bs, 1);
-            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
-            bs += __shfl_xor_sync(0xffffffffu, bs, 2);
-            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
-            if (!act[u]) continue;
-            int e = (int)((__float_as_uint(bm) >> 23) & 0xFF) - 127;
-            if (!(bm > 0.0f) || bm > 3.0e38f) e = 7;  // all-zero (or non-finite) block: scale 1
-            e = e < -100 ? -100 : (e > 100 ? 100 : e);
-            const float s = __uint_as_float((uint32_t)(7 - e + 127) << 23);
-            const float inv = __uint_as_float((uint32_t)(17 + e + 127) << 23);  // 2^24 / s
-            const float ev[8] = {l.x * s, l.y * s, l.z * s, l.w * s,
-                                 h.x * s * 0.0625f, h.y * s * 0.0625f, h.z * s * 0.0625f, h.w * s * 0.0625f};
-            float hh[8], md[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                hh[q] = __half2float(__float2half_rn(ev[q]));
-                md[q] = ev[q] - hh[q];
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int o = 4 * j;
-                uint2 fh, fm;
-                fh.x = pack_h2(hh[o + 0], hh[o + 2]);
-                fh.y = pack_h2(hh[o + 1], hh[o + 3]);
-                fm.x = pack_h2(md[o + 0], md[o + 2]);
-                fm.y = pack_h2(md[o + 1], md[o + 3]);
-                uint2 *dst = bf + ((size_t)(bl[u] * 2 + j) * (2 * MT)) * 4;
-                dst[(2 * m + 0) * 4 + t] = fh;
-                dst[(2 * m + 1) * 4 + t] = fm;
-            }
-            if (t == 0) off2[bl[u] * MT + m] = make_float2(-8.0f * bs, inv);
-        }
+    for (int q = 0; q < 8; ++q) {
+        hh[q] = __half2float(__float2half_rn(ev[q]));
+        md[q] = ev[q] - hh[q];
     }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int o = 4 * j;
+        uint2 fh, fm;
+        fh.x = pack_h2(hh[o + 0], hh[o + 2]);
+        fh.y = pack_h2(hh[o + 1], hh[o + 3]);
+        fm.x = pack_h2(md[o + 0], md[o + 2]);
+        fm.y = pack_h2(md[o + 1], md[o + 3]);
+        uint2 *dst = bf_blk + (size_t)j * (2 * MT) * 4;
+        dst[(2 * m + 0) * 4 + t] = fh;
+        dst[(2 * m + 1) * 4 + t] = fm;
+    }
+    if (t == 0) off_blk[m] = make_float2(-8.0f * bs, inv);
 }
 
 template <int MT, int G, int DPL>
@@ -255,6 +238,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     float *rinv = reinterpret_cast<float *>(empty + MG_MAX_STAGES + 2);  // [8]
     float *red = rinv + 8;                                            // [2][MG_CWARPS][NT*16*MT]
     float *acc_tile = red + 2 * MG_CWARPS * NT * 16 * MT;             // [MG_ACC_TILES][16*MT]
+    float *vals = acc_tile + MG_ACC_TILES * 16 * MT;                  // [1 or 2 blocks][32][MT]
+    uint64_t *stg = empty + MG_MAX_STAGES;                            // activation fragments landed in scratch
     unsigned char *scratch = smem + mg_misc_bytes(MT);
     unsigned char *ring = scratch + p.scratch_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -268,6 +253,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], MG_CWARPS);
         }
+        mbar_init(stg, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -288,14 +274,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 if (oi + 1 < p.n_ops) {
                     const MegaOp &nx = p.ops[oi + 1];
                     if (nx.kind == MG_MATVEC && (oi % nctas) == cta && !(flags & 4)) {
-                        if (nx.gamma) bulk_prefetch_l2(nx.gamma, (uint32_t)nx.K * 4u);
+                        if (nx.fout_gamma) bulk_prefetch_l2(nx.fout_gamma, (uint32_t)nx.N * 4u);
                     }
                 }
                 if (op.kind != MG_MATVEC) continue;
-                const int n_tiles = op.n_tiles, n_pairs = op.n_pairs, S = op.S, Ps = op.Ps;
+                const int n_tiles = op.n_tiles, n_pairs = op.n_pairs, S = op.S, Ps = op.Ps, UT = op.unit_tiles;
                 const uint4 *qs = op.qs_tc;
                 const uint2 *ds = op.d_tc;
-                const int ntl = cta < n_tiles ? (n_tiles - cta + nctas - 1) / nctas : 0;
+                const int ntl = mg_tile_count(n_tiles, UT, cta, nctas);
                 for (int s = 0; s < S; ++s) {
                     const int pb = s * Ps;
                     const int np = min(Ps, n_pairs - pb);
@@ -307,7 +293,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                             unsigned char *dst = ring + (size_t)stage * (NT * MG_SLOT_BYTES);
                             mbar_expect_tx(&full[stage], (uint32_t)(nt * nb) * 576u);
                             for (int u = 0; u < nt; ++u) {
-                                const size_t pair0 = (size_t)(cta + (it + u) * nctas) * n_pairs + pb + c0;
+                                const size_t pair0 = (size_t)mg_tile_of(it + u, UT, cta, nctas) * n_pairs + pb + c0;
                                 if (flags & 1) {
                                     bulk_g2s(dst + (size_t)u * MG_SLOT_BYTES, qs + pair0 * 32, (uint32_t)nb * 512u, &full[stage]);
                                     bulk_g2s(dst + (size_t)u * MG_SLOT_BYTES + MG_SLOT_Q, ds + pair0 * 8, (uint32_t)nb * 64u, &full[stage]);
@@ -333,7 +319,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     const int pos = *p.d_pos;
     const int outpos = *p.d_outpos;
     int stage = 0;
-    uint32_t phase = 0;
+    uint32_t phase = 0, stg_phase = 0;
     int par = 0;
     unsigned bar_target = 0;
     float best_v = -INFINITY;
@@ -356,33 +342,39 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         }
         if (kind == MG_MATVEC) {
             const int n_tiles = op.n_tiles, n_pairs = op.n_pairs, S = op.S, Ps = op.Ps, N = op.N, K = op.K;
-            const int epi = op.epi, ldy = op.ldy, track = op.track_argmax;
+            const int epi = op.epi, ldy = op.ldy, track = op.track_argmax, UT = op.unit_tiles;
             const bool has_norm = op.gamma != nullptr;
             float *const yout = op.y;
             const float *const bias = op.bias, *const resid = op.res;
             float *const ssq_out = op.ssq_out;
-            const int ntl = cta < n_tiles ? (n_tiles - cta + nctas - 1) / nctas : 0;
+            uint2 *const fout_bf = op.fout_bf;
+            float2 *const fout_off = op.fout_off;
+            const float *const fout_gamma = op.fout_gamma;
+            const int ntl = mg_tile_count(n_tiles, UT, cta, nctas);
             float2 *off2 = reinterpret_cast<float2 *>(scratch);             // [2*Ps][MT]
             uint2 *bf = reinterpret_cast<uint2 *>(off2 + (size_t)Ps * 2 * MT);  // [2*Ps][2][2*MT][4]
             if (ntl > 0) {
                 for (int s = 0; s < S; ++s) {
                     const int pb = s * Ps;
                     const int np = min(Ps, n_pairs - pb);
-                    // row statistics of the fused RMSNorm: the loads are issued before the staging pass and
-                    // consumed after it (the epilogue is their first user)
-                    const bool stats = (s == 0) && has_norm && warp < B;
-                    float pr[8];
-                    if (stats) {
+                    cbar();  // every warp is done with the previous contents of scratch
+                    if (tid == 0) {
+                        // the input's fragments were written (generic proxy, other SMs) before the grid barrier
+                        asm volatile("fence.proxy.async;\n" ::: "memory");
+                        const uint32_t ob = (uint32_t)(2 * np * MT) * 8u, bb = (uint32_t)(2 * np * MT) * 128u;
+                        mbar_expect_tx(stg, ob + bb);
+                        bulk_g2s(off2, op.fin_off + (size_t)(2 * pb) * MT, ob, stg);
+                        bulk_g2s(bf, op.fin_bf + (size_t)(2 * pb) * (16 * MT), bb, stg);
+                    }
+                    // row statistics of the fused RMSNorm (first used by the epilogue)
+                    if (s == 0 && has_norm && warp < B) {
+                        float ss = 0.0f;
+                        float pr[8];
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const int i = lane + 32 * q;
                             pr[q] = i < op.ssq_in_parts ? __ldcg(op.ssq_in + (size_t)i * B + warp) : 0.0f;
                         }
-                    }
-                    cbar();  // every warp is done with the previous contents of scratch
-                    mg_stage<MT>(op.x, K, B, op.gamma, pb * 2, np * 2, bf, off2);
-                    if (stats) {
-                        float ss = 0.0f;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) ss += pr[q];
                         for (int i = lane + 256; i < op.ssq_in_parts; i += 32) ss += __ldcg(op.ssq_in + (size_t)i * B + warp);
@@ -390,10 +382,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
                         if (lane == 0) rinv[warp] = 1.0f / sqrtf(ss / (float)K + p.eps);
                     }
-                    cbar();
+                    mbar_wait(stg, stg_phase, wd_flag, 0x500u + (unsigned)oi);
+                    stg_phase ^= 1u;
+                    cbar();  // rinv visible to the epilogue threads
                     if (tracing && s == 0) p.trace[oi * 6 + 1] = (unsigned long long)clock64();
-                    // the CTA's tiles (cta, cta+grid, ...) NT at a time: every warp carries NT independent
-                    // accumulation chains that share one read of the activation fragments
+                    // the CTA's tiles NT at a time: every warp carries NT independent accumulation chains that
+                    // share one read of the activation fragments
                     for (int it = 0; it < ntl; it += NT) {
                         const int nt = min(NT, ntl - it);
                         float acc[NT][CG][2];
@@ -403,7 +397,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                             for (int c = 0; c < CG; ++c) acc[u][c][0] = acc[u][c][1] = 0.0f;
                         // reducer threads: (tile slot, token, row) = (tid / 16MT, (tid % 16MT) / 16, tid % 16)
                         const int r_slot = tid / (16 * MT), r_tok = (tid % (16 * MT)) >> 4, r_r = tid & 15;
-                        const int r_tile = cta + (it + r_slot) * nctas;
+                        const int r_tile = mg_tile_of(it + r_slot, UT, cta, nctas);
                         const int r_row = r_tile * 16 + r_r;
                         const bool r_valid = tid < NT * 16 * MT && r_slot < nt;
                         // the epilogue's residual operand: fetched now, used after the tile's weight stream
@@ -455,12 +449,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                                             const uint32_t a_hi[4] = {wg & 0x00F000F0u, wg8 & 0x00F000F0u, sg & 0x00F000F0u, sg8 & 0x00F000F0u};
 #pragma unroll
                                             for (int c = 0; c < CG; ++c) {
-                                                // two independent MMAs (low / high nibbles), summed afterwards
-                                                float cl[4] = {0.f, 0.f, 0.f, 0.f}, ch[4] = {0.f, 0.f, 0.f, 0.f};
-                                                mma16816(cl, a_lo[0], a_lo[1], a_lo[2], a_lo[3], blo[c].x, blo[c].y);
-                                                mma16816(ch, a_hi[0], a_hi[1], a_hi[2], a_hi[3], bhi[c].x, bhi[c].y);
-                                                acc[u][c][0] = fmaf(d0, fmaf((cl[0] + ch[0]) + (cl[1] + ch[1]), of[c].y, of[c].x), acc[u][c][0]);
-                                                acc[u][c][1] = fmaf(d1, fmaf((cl[2] + ch[2]) + (cl[3] + ch[3]), of[c].y, of[c].x), acc[u][c][1]);
+                                                // low and high nibbles accumulate into one tile (the NT tiles give the ILP)
+                                                float cc[4] = {0.f, 0.f, 0.f, 0.f};
+                                                mma16816(cc, a_lo[0], a_lo[1], a_lo[2], a_lo[3], blo[c].x, blo[c].y);
+                                                mma16816(cc, a_hi[0], a_hi[1], a_hi[2], a_hi[3], bhi[c].x, bhi[c].y);
+                                                acc[u][c][0] = fmaf(d0, fmaf(cc[0] + cc[1], of[c].y, of[c].x), acc[u][c][0]);
+                                                acc[u][c][1] = fmaf(d1, fmaf(cc[2] + cc[3], of[c].y, of[c].x), acc[u][c][1]);
                                             }
                                         }
                                     }
@@ -505,19 +499,23 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                             if (s + 1 == S) {
                                 const bool live = r_valid && r_tok < B;
                                 if (has_norm && live) v *= rinv[r_tok];
+                                float fval = 0.0f;  // what the next matvec consumes (0 for padding rows)
                                 if (epi == EPI_SILU_MUL) {
                                     const float o = __shfl_xor_sync(0xffffffffu, v, 1);
-                                    if (live && !(r_r & 1) && r_row + 1 < N)
-                                        yout[(size_t)r_tok * ldy + (r_row >> 1)] = (v / (1.0f + expf(-v))) * o;
+                                    if (live && !(r_r & 1) && r_row + 1 < N) {
+                                        fval = (v / (1.0f + expf(-v))) * o;
+                                        if (yout) yout[(size_t)r_tok * ldy + (r_row >> 1)] = fval;
+                                    }
                                 } else {
                                     float out = 0.0f;
                                     if (live && r_row < N) {
                                         out = v + (bias ? bias[r_row] : 0.0f);
                                         if (epi == EPI_RESIDUAL) out += res_pre;
                                         if (epi == EPI_GELU) out = 0.5f * out * (1.0f + erff(out * 0.70710678118654752440f));
-                                        yout[(size_t)r_tok * ldy + r_row] = out;
+                                        if (yout) yout[(size_t)r_tok * ldy + r_row] = out;
                                         if (track) amax_combine(best_v, best_i, out, r_row);
                                     }
+                                    fval = out;
                                     if (ssq_out) {
                                         float sq = out * out;
                                         sq += __shfl_xor_sync(0xffffffffu, sq, 8);
@@ -527,12 +525,48 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                                         if (live && r_r == 0) ssq_out[(size_t)r_tile * B + r_tok] = sq;
                                     }
                                 }
+                                if (fout_bf) {
+                                    // ---- this group's outputs become the next matvec's activation fragments:
+                                    // a unit of UT consecutive tiles = one 32-value block per token
+                                    const int li = it + r_slot;                       // index in the CTA's tile list
+                                    const int be = UT <= NT ? r_slot / UT : 0;        // block within this group
+                                    const int ti = li % UT;                           // tile within its unit
+                                    rbar<RW>();  // the previous group's builders are done with vals
+                                    if (live) {
+                                        if (epi == EPI_SILU_MUL) {
+                                            if (!(r_r & 1)) vals[(be * 32 + ti * 8 + (r_r >> 1)) * MT + r_tok] = fval;
+                                        } else {
+                                            vals[(be * 32 + ti * 16 + r_r) * MT + r_tok] = fval;
+                                        }
+                                    }
+                                    rbar<RW>();
+                                    const int nblk = UT <= NT ? nt / UT : (((it + NT) % UT == 0) ? 1 : 0);
+                                    const int bi = tid / (4 * MT), bm_ = (tid % (4 * MT)) >> 2, bt = tid & 3;
+                                    const bool bact = bi < nblk && bm_ < B;
+                                    if (tid < ((2 * 4 * MT + 31) / 32) * 32) {  // warp-uniform: the warps holding builder lanes
+                                        const int lb = UT <= NT ? it + bi * UT : it + NT - UT;  // list index of the block's first tile
+                                        const int blk = cta + (lb / UT) * nctas;                // unit index = block index
+                                        float4 l = make_float4(0.f, 0.f, 0.f, 0.f), h = l;
+                                        if (bact) {
+                                            const float *vb = vals + (size_t)(bi * 32) * MT + bm_;
+                                            l = make_float4(vb[(4 * bt + 0) * MT], vb[(4 * bt + 1) * MT], vb[(4 * bt + 2) * MT], vb[(4 * bt + 3) * MT]);
+                                            h = make_float4(vb[(16 + 4 * bt + 0) * MT], vb[(16 + 4 * bt + 1) * MT], vb[(16 + 4 * bt + 2) * MT],
+                                                            vb[(16 + 4 * bt + 3) * MT]);
+                                            if (fout_gamma) {
+                                                l = mul4(l, *reinterpret_cast<const float4 *>(fout_gamma + (size_t)blk * 32 + 4 * bt));
+                                                h = mul4(h, *reinterpret_cast<const float4 *>(fout_gamma + (size_t)blk * 32 + 16 + 4 * bt));
+                                            }
+                                        }
+                                        frag_build<MT>(l, h, bact, bt, bm_, fout_bf + (size_t)blk * (16 * MT), fout_off + (size_t)blk * MT);
+                                    }
+                                }
                             }
                         }
                         par ^= 1;
                     }
                 }
             }
+            if (fout_bf) asm volatile("fence.proxy.async;\n" ::: "memory");  // fragments are read by bulk copies next phase
             if (track && warp < RW) {
                 // this CTA's best candidate per stream (lowest index wins ties: order independent):
                 // first the 16 rows of a (slot, token) group, then the NT slots through shared memory
@@ -730,16 +764,20 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 const int kvh = hh / G, h = hh - kvh * G;
                 const size_t u0 = ((size_t)b * Hkv + kvh) * NC;
                 float mc[16], lc[16], ac[16];
-                float mx = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
+                for (int c = 0; c < 16; ++c) {  // all loads first (in-order issue: a use would serialise them)
+                    mc[c] = -INFINITY;
+                    lc[c] = 0.0f;
+                    ac[c] = 0.0f;
                     if (c < NC) {
                         mc[c] = __ldcg(p.att_ml + ((u0 + c) * G + h) * 2 + 0);
                         lc[c] = __ldcg(p.att_ml + ((u0 + c) * G + h) * 2 + 1);
                         ac[c] = __ldcg(p.att_acc + ((u0 + c) * G + h) * HD + d);
-                        mx = fmaxf(mx, mc[c]);
                     }
                 }
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) mx = fmaxf(mx, mc[c]);
                 float num = 0.0f, den = 0.0f;
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
@@ -749,12 +787,29 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         den = fmaf(lc[c], f, den);
                     }
                 }
-                p.attn_out[e] = num / den;
+                const float o = num / den;
+                p.attn_out[e] = o;
+                // a warp holds 32 consecutive head dims of one (stream, head) = one block of wo's input
+                const int bt = lane & 3;
+                float4 l, hq;
+                l.x = __shfl_sync(0xffffffffu, o, 4 * bt + 0);
+                l.y = __shfl_sync(0xffffffffu, o, 4 * bt + 1);
+                l.z = __shfl_sync(0xffffffffu, o, 4 * bt + 2);
+                l.w = __shfl_sync(0xffffffffu, o, 4 * bt + 3);
+                hq.x = __shfl_sync(0xffffffffu, o, 16 + 4 * bt + 0);
+                hq.y = __shfl_sync(0xffffffffu, o, 16 + 4 * bt + 1);
+                hq.z = __shfl_sync(0xffffffffu, o, 16 + 4 * bt + 2);
+                hq.w = __shfl_sync(0xffffffffu, o, 16 + 4 * bt + 3);
+                const int blk = ((e - lane) % (H * HD)) >> 5;
+                frag_build<MT>(l, hq, lane < 4, bt, b, p.att_fbf + (size_t)blk * (16 * MT), p.att_foff + (size_t)blk * MT);
             }
+            asm volatile("fence.proxy.async;\n" ::: "memory");
         } else if (kind == MG_EMBED) {
             // x_dec[b] = audio[b][pos] + dequant(E[tok[b]])   (model.rs:584-618, 938-946)
             const int D = p.D, bpr = D >> 5, n = bpr * 16;
+            float *xr = reinterpret_cast<float *>(scratch);  // the embedded row, for the fragment builders
             for (int b = cta; b < B; b += nctas) {
+                cbar();
                 const int id = p.d_tok[b];
                 const float *arow = p.audio ? p.audio + ((size_t)b * p.audio_seq + pos) * D : nullptr;
                 for (int base = 0; base < n; base += MG_CTHREADS) {
@@ -774,6 +829,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         }
                         p.x_dec[(size_t)b * D + k] = lo;
                         p.x_dec[(size_t)b * D + k + 16] = hi;
+                        xr[k] = lo;
+                        xr[k + 16] = hi;
                     }
                     float sl = lo * lo, sh = hi * hi;
 #pragma unroll
@@ -786,7 +843,25 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         p.ssq_x[(size_t)(2 * blk + 1) * B + b] = sh;
                     }
                 }
+                cbar();
+                // fragments of (row x first layer's attention-norm weight) for layer 0's wqkv
+                for (int base = 0; base < bpr * 4; base += MG_CTHREADS) {
+                    const int i = base + tid;
+                    const bool act = i < bpr * 4;
+                    const int blk = act ? i >> 2 : 0, bt = i & 3;
+                    float4 l = make_float4(0.f, 0.f, 0.f, 0.f), h = l;
+                    if (act) {
+                        l = *reinterpret_cast<const float4 *>(xr + blk * 32 + 4 * bt);
+                        h = *reinterpret_cast<const float4 *>(xr + blk * 32 + 16 + 4 * bt);
+                        if (p.emb_gamma) {
+                            l = mul4(l, *reinterpret_cast<const float4 *>(p.emb_gamma + blk * 32 + 4 * bt));
+                            h = mul4(h, *reinterpret_cast<const float4 *>(p.emb_gamma + blk * 32 + 16 + 4 * bt));
+                        }
+                    }
+                    frag_build<MT>(l, h, act, bt, b, p.emb_fbf + (size_t)blk * (16 * MT), p.emb_foff + (size_t)blk * MT);
+                }
             }
+            asm volatile("fence.proxy.async;\n" ::: "memory");
         } else {  // MG_ARGMAX
             if (cta == 0) {
                 if (warp < B) {

@@ -24,8 +24,17 @@ struct MegaOp {
     const uint2 *d_tc = nullptr;
     int N = 0, K = 0, n_tiles = 0, n_pairs = 0;
     int S = 1, Ps = 0;  // CTA-private K slices: the activation fragments of one slice fit the scratch region
-    const float *x = nullptr;
-    float *y = nullptr;
+    // activation fragments (tensor-core B operands + per-block offsets, see decode_mega.cu) of the input,
+    // written by the phase that produced the activations; bulk-copied into shared memory, never re-derived
+    const uint2 *fin_bf = nullptr;    // [K/32 (+pad)][2][2*MT][4]
+    const float2 *fin_off = nullptr;  // [K/32 (+pad)][MT]
+    // fragments of this op's OUTPUT for the next matvec (nullptr: plain output only): one 32-value block per
+    // unit of `unit_tiles` consecutive tiles (2: plain rows, 4: SiLU pairs), scaled by fout_gamma if set
+    uint2 *fout_bf = nullptr;
+    float2 *fout_off = nullptr;
+    const float *fout_gamma = nullptr;
+    int unit_tiles = 1;
+    float *y = nullptr;               // plain output (nullptr: fragments only)
     int ldy = 0;
     const float *bias = nullptr, *res = nullptr;
     const float *gamma = nullptr;   // fused RMSNorm weight (x ADA scale where the layer has one)
@@ -58,6 +67,11 @@ struct MegaParams {
     const float *audio = nullptr;
     int audio_seq = 0;
     float *x_dec = nullptr, *ssq_x = nullptr;
+    uint2 *emb_fbf = nullptr;         // fragments of the embedded row (x first layer's attn_norm) for layer 0
+    float2 *emb_foff = nullptr;
+    const float *emb_gamma = nullptr;
+    uint2 *att_fbf = nullptr;         // fragments of the attention output (input of wo)
+    float2 *att_foff = nullptr;
     // device-side step state
     int *d_pos = nullptr, *d_outpos = nullptr, *d_tok = nullptr, *d_out = nullptr;
     int out_ld = 0;

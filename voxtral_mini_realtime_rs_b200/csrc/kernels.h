@@ -91,6 +91,10 @@ void launch_rope_inplace(float *buf, int rows, int ld, int q_off, int n_q, int k
 // [B*S][ld] with q at q_off, k at k_off, v at v_off; out [B*S][H*hd].
 void launch_enc_attention(const float *qkv, float *out, int B, int S, int H, int hd, int ld, int q_off,
                           int k_off, int v_off, int window, float scale, cudaStream_t st);
+// same contract on the tensor cores (enc_attn_tc.cu): mma.sync with two-piece f16 operands, f32-grade accuracy
+bool enc_attention_tc_supported(int hd, int ld, int q_off, int k_off, int v_off);
+void launch_enc_attention_tc(const float *qkv, float *out, int B, int S, int H, int hd, int ld, int q_off,
+                             int k_off, int v_off, int window, float scale, cudaStream_t st);
 // decoder: RoPE q in place, RoPE k -> Kcache, v -> Vcache at positions *pos_ptr + i.
 // qkv rows [B*M][ld]; caches [B][Hkv][max_seq][hd].
 void launch_dec_rope_append(float *qkv, int B, int M, int ld, int H, int Hkv, int hd, float *kc, float *vc,

@@ -443,6 +443,8 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
             s->xt_buf = s->arena.alloc(e * 2);
             const char *gv = getenv("VOX_GEMM");
             s->use_gemm_tc = !(gv && std::string(gv) == "simt");
+            const char *av = getenv("VOX_ENC_ATTN");
+            s->use_enc_attn_tc = !(av && std::string(av) == "simt");
         }
         {   // fused-decode scratch (see TcWork): sized for the largest split-K matvec at max_batch rows
             const int mb = std::min(8, max_batch * 1);
@@ -473,6 +475,7 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
         {   // persistent decode-step kernel
             const char *mv = getenv("VOX_MEGA");
             s->use_mega = !(mv && mv[0] == '0');
+            if (const char *mb = getenv("VOX_MEGA_MIN_B")) s->mega_min_B = atoi(mb);
             s->mega_grid = decode_mega_grid(m->device);
             s->mega_ops_cap = 6 * c.dec_layers + 4;
             s->mega_ops = s->arena.alloc_n<MegaOp>(s->mega_ops_cap);
@@ -483,6 +486,18 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
             s->mega_att_units = std::max(s->mega_grid, 8 * c.dec_kv_heads) + 8 * c.dec_kv_heads;
             s->mega_att_acc = s->arena.alloc_n<float>((size_t)s->mega_att_units * (c.dec_heads / c.dec_kv_heads) * c.dec_head_dim);
             s->mega_att_ml = s->arena.alloc_n<float>((size_t)s->mega_att_units * (c.dec_heads / c.dec_kv_heads) * 2);
+            {
+                auto blocks = [](int K) { return (size_t)((K / 32 + 1) / 2) * 2; };
+                s->mega_xf_blocks = blocks(c.dec_dim);
+                s->mega_af_blocks = blocks(c.dec_heads * c.dec_head_dim);
+                s->mega_cf_blocks = blocks(c.dec_ffn);
+                s->mega_xf_bf = s->arena.alloc_n<uint2>(s->mega_xf_blocks * 16 * 8);
+                s->mega_af_bf = s->arena.alloc_n<uint2>(s->mega_af_blocks * 16 * 8);
+                s->mega_cf_bf = s->arena.alloc_n<uint2>(s->mega_cf_blocks * 16 * 8);
+                s->mega_xf_off = s->arena.alloc_n<float2>(s->mega_xf_blocks * 8);
+                s->mega_af_off = s->arena.alloc_n<float2>(s->mega_af_blocks * 8);
+                s->mega_cf_off = s->arena.alloc_n<float2>(s->mega_cf_blocks * 8);
+            }
             s->mega_trace = s->arena.alloc_n<unsigned long long>((size_t)s->mega_ops_cap * 6);
             CUDA_OK(cudaMemset(s->mega_trace, 0, sizeof(unsigned long long) * s->mega_ops_cap * 6));
         }
@@ -569,8 +584,12 @@ void Session::encode(int B, int T) {
         linear_n(l.wqkv, x_enc, rows, qkv_enc, 3 * hdq, l.bqkv, nullptr, EPI_NONE, l.attn_norm, nullptr, h_enc);
         launch_rope_inplace(qkv_enc, rows, 3 * hdq, 0, c.enc_heads, hdq, c.enc_heads, c.enc_head_dim, S, 0,
                             m->enc_cos, m->enc_sin, st);
-        launch_enc_attention(qkv_enc, attn_enc, B, S, c.enc_heads, c.enc_head_dim, 3 * hdq, 0, hdq, 2 * hdq,
-                             c.enc_window, scale, st);
+        if (use_enc_attn_tc && enc_attention_tc_supported(c.enc_head_dim, 3 * hdq, 0, hdq, 2 * hdq))
+            launch_enc_attention_tc(qkv_enc, attn_enc, B, S, c.enc_heads, c.enc_head_dim, 3 * hdq, 0, hdq, 2 * hdq,
+                                    c.enc_window, scale, st);
+        else
+            launch_enc_attention(qkv_enc, attn_enc, B, S, c.enc_heads, c.enc_head_dim, 3 * hdq, 0, hdq, 2 * hdq,
+                                 c.enc_window, scale, st);
         linear(l.wo, attn_enc, rows, x_enc, d, l.bo, x_enc, EPI_RESIDUAL);
         linear_n(l.w13, x_enc, rows, act_enc, c.enc_ffn, nullptr, nullptr, EPI_SILU_MUL, l.ffn_norm, nullptr, h_enc);
         linear(l.w2, act_enc, rows, x_enc, d, l.b2, x_enc, EPI_RESIDUAL);
@@ -671,7 +690,7 @@ void Session::lm_head_rows(int rows, bool norm_pending, float *dst) {
 // the shapes are outside what decode_mega.cu is instantiated for; the caller then uses per-op launches.
 bool Session::mega_prepare(int B) {
     const vox_model_info &c = m->info;
-    if (!use_mega || !use_tc || !fused_decode(B)) return false;
+    if (!use_mega || !use_tc || !fused_decode(B) || B < mega_min_B) return false;
     if (!decode_mega_supported(B, c.dec_heads, c.dec_kv_heads, c.dec_head_dim)) return false;
     if (mega_B == B) return mega_n_ops > 0;
     mega_B = B;
@@ -687,8 +706,11 @@ bool Session::mega_prepare(int B) {
     const int parts = (D + 15) / 16;
     std::vector<MegaOp> ops;
     bool ok = true;
-    auto matvec = [&](const Q4Weight &w, const float *x, float *y, int ldy, const float *res, int epi, const float *gamma,
-                      bool ssq_out_, bool track) {
+    const int MT = mega_plan.MT;
+    struct Frag { uint2 *bf; float2 *off; };
+    const Frag XF{mega_xf_bf, mega_xf_off}, AF{mega_af_bf, mega_af_off}, CF{mega_cf_bf, mega_cf_off};
+    auto matvec = [&](const Q4Weight &w, Frag fin, float *y, int ldy, const float *res, int epi, const float *norm_w,
+                      bool ssq_out_, bool track, int unit_tiles, Frag fout, const float *fout_gamma) {
         MegaOp o;
         o.kind = MG_MATVEC;
         o.epi = epi;
@@ -704,13 +726,21 @@ bool Session::mega_prepare(int B) {
         S = (o.n_pairs + Ps - 1) / Ps;
         o.S = S;
         o.Ps = Ps;
-        if (S > 1 && (o.n_tiles + mega_grid - 1) / mega_grid > 4) ok = false;  // tile sums kept across slices: 4 per CTA
-        o.x = x;
+        o.unit_tiles = unit_tiles;
+        if (o.n_tiles % unit_tiles != 0) ok = false;
+        const int n_units = o.n_tiles / unit_tiles;
+        // tile sums kept in shared memory across K slices: 2 tiles per CTA
+        if (S > 1 && ((n_units + mega_grid - 1) / mega_grid) * unit_tiles > 2) ok = false;
+        o.fin_bf = fin.bf;
+        o.fin_off = fin.off;
+        o.fout_bf = fout.bf;
+        o.fout_off = fout.off;
+        o.fout_gamma = fout_gamma;
         o.y = y;
         o.ldy = ldy;
         o.res = res;
-        o.gamma = gamma;
-        if (gamma) {
+        o.gamma = norm_w;  // != nullptr: the input is RMS-normalised (1/rms applied in the epilogue)
+        if (norm_w) {
             o.ssq_in = ssq_x;
             o.ssq_in_parts = parts;
         }
@@ -718,6 +748,7 @@ bool Session::mega_prepare(int B) {
         o.track_argmax = track ? 1 : 0;
         ops.push_back(o);
     };
+    const Frag none{nullptr, nullptr};
     {
         MegaOp e;
         e.kind = MG_EMBED;
@@ -725,7 +756,7 @@ bool Session::mega_prepare(int B) {
     }
     for (int j = 0; j < c.dec_layers; ++j) {
         const DecLayerW &l = m->dec[j];
-        matvec(l.wqkv, x_dec, qkv_dec, qkvd, nullptr, EPI_NONE, l.attn_norm, false, false);
+        matvec(l.wqkv, XF, qkv_dec, qkvd, nullptr, EPI_NONE, l.attn_norm, false, false, 1, none, nullptr);
         MegaOp a;
         a.kind = MG_ATTN;
         a.kc = kc + (size_t)j * layer_stride;
@@ -734,19 +765,32 @@ bool Session::mega_prepare(int B) {
         MegaOp am;
         am.kind = MG_ATTN_MERGE;
         ops.push_back(am);
-        matvec(l.wo, attn_dec, x_dec, D, x_dec, EPI_RESIDUAL, nullptr, true, false);
-        matvec(l.w13, x_dec, act_dec, c.dec_ffn, nullptr, EPI_SILU_MUL, ffn_gamma_ada + (size_t)j * D, false, false);
-        matvec(l.w2, act_dec, x_dec, D, x_dec, EPI_RESIDUAL, nullptr, true, false);
+        // wo: h += attn . Wo^T; leaves fragments of h x (ffn_norm x ADA) for w13
+        matvec(l.wo, AF, x_dec, D, x_dec, EPI_RESIDUAL, nullptr, true, false, 2, XF, ffn_gamma_ada + (size_t)j * D);
+        // w13: SwiGLU of the normed stream; leaves fragments of the activation for w2 (no plain copy)
+        matvec(l.w13, XF, nullptr, c.dec_ffn, nullptr, EPI_SILU_MUL, l.ffn_norm, false, false, 4, CF, nullptr);
+        // w2: h += act . W2^T; leaves fragments of h x (next attention norm | final norm)
+        const float *next_norm = j + 1 < c.dec_layers ? m->dec[j + 1].attn_norm : m->dec_norm;
+        matvec(l.w2, CF, x_dec, D, x_dec, EPI_RESIDUAL, nullptr, true, false, 2, XF, next_norm);
     }
-    matvec(m->tok_emb, x_dec, logits, c.vocab, nullptr, EPI_NONE, m->dec_norm, false, true);
+    matvec(m->tok_emb, XF, logits, c.vocab, nullptr, EPI_NONE, m->dec_norm, false, true, 1, none, nullptr);
     {
         MegaOp f;
         f.kind = MG_ARGMAX;
         ops.push_back(f);
     }
+    (void)MT;
+    if (c.dec_ffn % 32 != 0 || (H * hd) % 32 != 0) ok = false;
     // the residual epilogues and the embedding must leave exactly `parts` partial sums of squares
     if ((D + 15) / 16 != parts || D % 32 != 0) ok = false;
     if (!ok || (int)ops.size() > mega_ops_cap) return false;
+    // padding tokens (capacity MT > B) and padding blocks must read as zero fragments
+    CUDA_OK(cudaMemsetAsync(mega_xf_bf, 0, sizeof(uint2) * mega_xf_blocks * 16 * 8, st));
+    CUDA_OK(cudaMemsetAsync(mega_af_bf, 0, sizeof(uint2) * mega_af_blocks * 16 * 8, st));
+    CUDA_OK(cudaMemsetAsync(mega_cf_bf, 0, sizeof(uint2) * mega_cf_blocks * 16 * 8, st));
+    CUDA_OK(cudaMemsetAsync(mega_xf_off, 0, sizeof(float2) * mega_xf_blocks * 8, st));
+    CUDA_OK(cudaMemsetAsync(mega_af_off, 0, sizeof(float2) * mega_af_blocks * 8, st));
+    CUDA_OK(cudaMemsetAsync(mega_cf_off, 0, sizeof(float2) * mega_cf_blocks * 8, st));
     mega_ops_host = ops;
     CUDA_OK(cudaMemcpyAsync(mega_ops, mega_ops_host.data(), sizeof(MegaOp) * ops.size(), cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaStreamSynchronize(st));
@@ -785,6 +829,11 @@ void Session::decode_step(int B) {
         p.audio_seq = cur_S4;
         p.x_dec = x_dec;
         p.ssq_x = ssq_x;
+        p.emb_fbf = mega_xf_bf;
+        p.emb_foff = mega_xf_off;
+        p.emb_gamma = m->dec[0].attn_norm;
+        p.att_fbf = mega_af_bf;
+        p.att_foff = mega_af_off;
         p.d_pos = d_pos;
         p.d_outpos = d_outpos;
         p.d_tok = d_tok;

@@ -124,6 +124,7 @@ struct Session {
     // persistent decode-step kernel (decode_mega.cu): op table per batch size, grid barrier words,
     // per-CTA argmax candidates.  VOX_MEGA=0 (or debug "mega_off") selects the per-op launches.
     bool use_mega = true;
+    int mega_min_B = 2;  // a single stream is (slightly) faster through the per-op launches (profiles/README.md)
     int mega_B = 0, mega_grid = 0, mega_n_ops = 0, mega_ops_cap = 0;
     MegaPlan mega_plan;
     std::vector<MegaOp> mega_ops_host;
@@ -133,11 +134,16 @@ struct Session {
     int *mega_am_idx = nullptr;
     float *mega_att_acc = nullptr, *mega_att_ml = nullptr;  // key-chunk softmax states (MG_ATTN -> MG_ATTN_MERGE)
     int mega_att_units = 0;
+    // activation fragments (decode_mega.cu frag_build): residual stream x norm weight, attention output, SwiGLU output
+    uint2 *mega_xf_bf = nullptr, *mega_af_bf = nullptr, *mega_cf_bf = nullptr;
+    float2 *mega_xf_off = nullptr, *mega_af_off = nullptr, *mega_cf_off = nullptr;
+    size_t mega_xf_blocks = 0, mega_af_blocks = 0, mega_cf_blocks = 0;
     unsigned long long *mega_trace = nullptr;  // [mega_ops_cap][6] SM-clock stamps of CTA 0 (debug "mega_trace")
     bool mega_prepare(int B);
     bool fused_decode(int rows) const;
     void *xt_buf = nullptr;   // bf16 split tiles feeding the tcgen05 GEMM
     size_t xt_elems = 0;
+    bool use_enc_attn_tc = true;  // tensor-core encoder attention (VOX_ENC_ATTN=simt disables)
     bool use_gemm_tc = true;  // tcgen05 GEMM for M > 8 (VOX_GEMM=simt disables)
     // y = epi(norm(x) . W^T): RMSNorm fused into the operand split when the tcgen05 path applies,
     // else rmsnorm into `tmp` + linear()
