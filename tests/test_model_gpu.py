@@ -81,7 +81,7 @@ def test_encoder_attention_tensor_core_vs_simt(tiny_model, tiny_oracle):
     """enc_attn_tc.cu (mma.sync, two-piece f16 operands; default) against the f32 SIMT kernel and the oracle:
     same encoder output to f32 rounding noise, with the sliding window biting (window 20 < S)."""
     _, mel = _mel(5.0, seed=77)
-    exp = tiny_oracle.encode_audio(mel)
+    exp = tiny_oracle.encode_audio(mel).numpy()[None]
     tiny_model.debug("enc_attn_tc")
     got_tc = tiny_model.encode_audio(mel).copy()
     tiny_model.debug("enc_attn_simt")

@@ -328,7 +328,7 @@ static void q4_matmul_dispatch(const Q4Weight &w, const float *x, float *y, int 
             h->xt_elems = need;
         }
         launch_split_tiles(x, rows, w.K, nullptr, nullptr, 0.0f, h->xt, st);
-        launch_q4_gemm_tc5(w, h->xt, rows, y, w.N, bias, nullptr, EPI_NONE, st);
+        launch_q4_gemm_tc5(w, h->xt, rows, y, w.N, bias, nullptr, EPI_NONE, nullptr, st);
         return;
     }
     if (rows <= 8 && w.qs_tc && !simt)

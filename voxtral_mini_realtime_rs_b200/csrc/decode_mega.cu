@@ -404,6 +404,18 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         float res_pre = 0.0f;
                         if (epi == EPI_RESIDUAL && s + 1 == S && r_valid && r_tok < B && r_row < N)
                             res_pre = __ldcg(resid + (size_t)r_tok * ldy + r_row);
+                        // fragment builders: (block within this group, token, t); the consumer's norm weight for
+                        // the builder's 8 elements is fetched now as well
+                        const int bi = tid / (4 * MT), bm_ = (tid % (4 * MT)) >> 2, bt = tid & 3;
+                        const int f_nblk = UT <= NT ? nt / UT : (((it + NT) % UT == 0) ? 1 : 0);
+                        const int f_lb = UT <= NT ? it + bi * UT : it + NT - UT;  // list index of the block's first tile
+                        const int f_blk = cta + (f_lb / UT) * nctas;              // unit index = block index
+                        const bool bact = fout_bf != nullptr && s + 1 == S && bi < f_nblk && bm_ < B;
+                        float4 fg_lo = make_float4(1.f, 1.f, 1.f, 1.f), fg_hi = fg_lo;
+                        if (bact && fout_gamma) {
+                            fg_lo = *reinterpret_cast<const float4 *>(fout_gamma + (size_t)f_blk * 32 + 4 * bt);
+                            fg_hi = *reinterpret_cast<const float4 *>(fout_gamma + (size_t)f_blk * 32 + 16 + 4 * bt);
+                        }
                         for (int c0 = 0; c0 < np; c0 += MG_CHUNK) {
                             mbar_wait(&full[stage], phase, wd_flag, 0x200u + (unsigned)oi);
                             if (tracing && s == 0 && it == 0 && c0 == 0) p.trace[oi * 6 + 4] = (unsigned long long)clock64();
@@ -540,24 +552,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                                         }
                                     }
                                     rbar<RW>();
-                                    const int nblk = UT <= NT ? nt / UT : (((it + NT) % UT == 0) ? 1 : 0);
-                                    const int bi = tid / (4 * MT), bm_ = (tid % (4 * MT)) >> 2, bt = tid & 3;
-                                    const bool bact = bi < nblk && bm_ < B;
                                     if (tid < ((2 * 4 * MT + 31) / 32) * 32) {  // warp-uniform: the warps holding builder lanes
-                                        const int lb = UT <= NT ? it + bi * UT : it + NT - UT;  // list index of the block's first tile
-                                        const int blk = cta + (lb / UT) * nctas;                // unit index = block index
                                         float4 l = make_float4(0.f, 0.f, 0.f, 0.f), h = l;
                                         if (bact) {
                                             const float *vb = vals + (size_t)(bi * 32) * MT + bm_;
                                             l = make_float4(vb[(4 * bt + 0) * MT], vb[(4 * bt + 1) * MT], vb[(4 * bt + 2) * MT], vb[(4 * bt + 3) * MT]);
                                             h = make_float4(vb[(16 + 4 * bt + 0) * MT], vb[(16 + 4 * bt + 1) * MT], vb[(16 + 4 * bt + 2) * MT],
                                                             vb[(16 + 4 * bt + 3) * MT]);
-                                            if (fout_gamma) {
-                                                l = mul4(l, *reinterpret_cast<const float4 *>(fout_gamma + (size_t)blk * 32 + 4 * bt));
-                                                h = mul4(h, *reinterpret_cast<const float4 *>(fout_gamma + (size_t)blk * 32 + 16 + 4 * bt));
-                                            }
+                                            l = mul4(l, fg_lo);
+                                            h = mul4(h, fg_hi);
                                         }
-                                        frag_build<MT>(l, h, bact, bt, bm_, fout_bf + (size_t)blk * (16 * MT), fout_off + (size_t)blk * MT);
+                                        frag_build<MT>(l, h, bact, bt, bm_, fout_bf + (size_t)f_blk * (16 * MT), fout_off + (size_t)f_blk * MT);
                                     }
                                 }
                             }

@@ -102,6 +102,11 @@ struct G5Args {
     float *y;
     int ldy;
     const float *bias, *res;
+    // deterministic split-K (grid.z slices of KCs k-steps): partial tiles [z][tile][tok 128][feat 128],
+    // the last CTA of a tile to arrive (ticket) adds them in slice order and runs the epilogue
+    int SK, KCs;
+    float *partial;
+    int *counters;
 };
 
 template <int EPI>
@@ -137,10 +142,12 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
     const int gn = f0 + drow;
     const size_t xt_piece = (size_t)a.TT * a.KC * (G5_TILE_BYTES / 2);  // elements per split piece
 
-    for (int kc = 0; kc < a.KC; ++kc) {
-        const int s = kc & 1, use = kc >> 1;
+    const int kc_begin = blockIdx.z * a.KCs, kc_end = min(a.KC, kc_begin + a.KCs);
+    for (int kc = kc_begin; kc < kc_end; ++kc) {
+        const int it = kc - kc_begin;
+        const int s = it & 1, use = it >> 1;
         unsigned char *stage = smem + (size_t)s * G5_STAGE_BYTES;
-        if (kc >= G5_STAGES) {
+        if (it >= G5_STAGES) {
             mbar_wait(&done_bar[s], (uint32_t)((use - 1) & 1));  // MMAs that read this stage have retired
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         }
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
                 const uint64_t xm = umma_desc(base + 3 * G5_TILE_BYTES + koff, lbo, sbo);
                 const uint64_t xl = umma_desc(base + 4 * G5_TILE_BYTES + koff, lbo, sbo);
                 // smallest terms first
-                umma_bf16(tmem_d, wlo, xm, idesc, (kc | ks) != 0);
+                umma_bf16(tmem_d, wlo, xm, idesc, (it | ks) != 0);
                 umma_bf16(tmem_d, whi, xl, idesc, 1);
                 umma_bf16(tmem_d, wlo, xh, idesc, 1);
                 umma_bf16(tmem_d, whi, xm, idesc, 1);
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
     }
     // ---- wait for the last commit of each stage (covers every MMA issued before it)
     {
-        const int last = a.KC - 1;
+        const int last = kc_end - kc_begin - 1;
         for (int s = 0; s < G5_STAGES; ++s) {
             const int kc_s = ((last & 1) == s) ? last : last - 1;
             if (kc_s >= 0) mbar_wait(&done_bar[s], (uint32_t)((kc_s >> 1) & 1));
@@ -227,37 +234,81 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
     }
     // ---- epilogue: warp w reads TMEM lanes 32*(w%4).. (features), columns 64*(w/4).. (tokens)
     {
+        __shared__ int is_last;
         const int q4 = warp & 3, hcol = warp >> 2;
         const int feat = f0 + q4 * 32 + lane;
+        const int tile_id = blockIdx.y * gridDim.x + blockIdx.x, n_tile = gridDim.x * gridDim.y;
+        float *ptile = a.SK > 1 ? a.partial + ((size_t)blockIdx.z * n_tile + tile_id) * (G5_BM * G5_BN) : nullptr;
+        uint32_t r[2][32];
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
             const int col0 = hcol * 64 + cb * 32;
-            uint32_t r[32];
             const uint32_t taddr = tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "=r"(r[cb][0]), "=r"(r[cb][1]), "=r"(r[cb][2]), "=r"(r[cb][3]), "=r"(r[cb][4]), "=r"(r[cb][5]), "=r"(r[cb][6]),
+                  "=r"(r[cb][7]), "=r"(r[cb][8]), "=r"(r[cb][9]), "=r"(r[cb][10]), "=r"(r[cb][11]), "=r"(r[cb][12]), "=r"(r[cb][13]),
+                  "=r"(r[cb][14]), "=r"(r[cb][15]), "=r"(r[cb][16]), "=r"(r[cb][17]), "=r"(r[cb][18]), "=r"(r[cb][19]), "=r"(r[cb][20]),
+                  "=r"(r[cb][21]), "=r"(r[cb][22]), "=r"(r[cb][23]), "=r"(r[cb][24]), "=r"(r[cb][25]), "=r"(r[cb][26]), "=r"(r[cb][27]),
+                  "=r"(r[cb][28]), "=r"(r[cb][29]), "=r"(r[cb][30]), "=r"(r[cb][31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        }
+        bool run_epilogue = true;
+        if (a.SK > 1) {
+            // publish this slice's tile, take a ticket; the last arriver sums the slices in order
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    __stcg(ptile + (size_t)(hcol * 64 + cb * 32 + j) * G5_BM + q4 * 32 + lane, __uint_as_float(r[cb][j]));
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                const int old = atomicAdd(&a.counters[tile_id], 1);
+                const int last = (old == a.SK - 1);
+                if (last) {
+                    a.counters[tile_id] = 0;
+                    __threadfence();
+                }
+                is_last = last;
+            }
+            __syncthreads();
+            run_epilogue = is_last != 0;
+            if (run_epilogue) {
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float v = 0.0f;
+                        for (int z = 0; z < a.SK; ++z)
+                            v += __ldcg(a.partial + ((size_t)z * n_tile + tile_id) * (G5_BM * G5_BN) +
+                                        (size_t)(hcol * 64 + cb * 32 + j) * G5_BM + q4 * 32 + lane);
+                        r[cb][j] = __float_as_uint(v);
+                    }
+            }
+        }
+        if (run_epilogue) {
             const float bsv = (a.bias && feat < a.N) ? a.bias[feat] : 0.0f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int tok = tok0 + col0 + j;
-                float v = __uint_as_float(r[j]);
-                if (EPI == EPI_SILU_MUL) {
-                    // features (2i, 2i+1) = (gate, up) sit in adjacent lanes
-                    const float other = __shfl_xor_sync(0xffffffffu, v, 1);
-                    if ((lane & 1) == 0 && tok < a.M && feat + 1 < a.N)
-                        a.y[(size_t)tok * a.ldy + (feat >> 1)] = (v / (1.0f + expf(-v))) * other;
-                } else if (tok < a.M && feat < a.N) {
-                    v += bsv;
-                    if (EPI == EPI_RESIDUAL) v += a.res[(size_t)tok * a.ldy + feat];
-                    if (EPI == EPI_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-                    a.y[(size_t)tok * a.ldy + feat] = v;
+            for (int cb = 0; cb < 2; ++cb) {
+                const int col0 = hcol * 64 + cb * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int tok = tok0 + col0 + j;
+                    float v = __uint_as_float(r[cb][j]);
+                    if (EPI == EPI_SILU_MUL) {
+                        // features (2i, 2i+1) = (gate, up) sit in adjacent lanes
+                        const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+                        if ((lane & 1) == 0 && tok < a.M && feat + 1 < a.N)
+                            a.y[(size_t)tok * a.ldy + (feat >> 1)] = (v / (1.0f + expf(-v))) * other;
+                    } else if (tok < a.M && feat < a.N) {
+                        v += bsv;
+                        if (EPI == EPI_RESIDUAL) v += a.res[(size_t)tok * a.ldy + feat];
+                        if (EPI == EPI_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+                        a.y[(size_t)tok * a.ldy + feat] = v;
+                    }
                 }
             }
         }
@@ -361,7 +412,7 @@ void launch_split_tiles(const float *x, int M, int K, const float *gamma, const 
 }
 
 void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int ldy, const float *bias, const float *res,
-                        int epi, cudaStream_t st) {
+                        int epi, const GemmWork *gw, cudaStream_t st) {
     VOX_CHECK(gemm_tc5_supported(w, M), VOX_EINVAL, "gemm_tc5: unsupported shape N=%d K=%d", w.N, w.K);
     G5Args a{};
     a.qs = w.qs;
@@ -377,7 +428,22 @@ void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int 
     a.bias = bias;
     a.res = res;
     const size_t smem = (size_t)G5_STAGES * G5_STAGE_BYTES + 1024;
-    dim3 grid(w.N / G5_BM, a.TT);
+    // split K when the output tiles alone cannot fill the GPU (single-stream encode: N = 1280 -> 50 tiles;
+    // prefill: 38 tokens -> one token tile)
+    const int tiles = (w.N / G5_BM) * a.TT;
+    int SK = 1;
+    if (gw && gw->partial && gw->counters && tiles < 100) {
+        SK = 148 / tiles;
+        SK = SK > 8 ? 8 : SK;
+        while (SK > 1 && a.KC / SK < 4) --SK;
+        while (SK > 1 && ((size_t)SK * tiles * G5_BM * G5_BN > gw->partial_floats || tiles > gw->n_counters)) --SK;
+    }
+    a.KCs = (a.KC + SK - 1) / SK;
+    SK = (a.KC + a.KCs - 1) / a.KCs;
+    a.SK = SK;
+    a.partial = SK > 1 ? gw->partial : nullptr;
+    a.counters = SK > 1 ? gw->counters : nullptr;
+    dim3 grid(w.N / G5_BM, a.TT, SK);
 #define G5_CASE(E)                                                                                              \
     case E: {                                                                                                   \
         static bool set = false;                                                                                \

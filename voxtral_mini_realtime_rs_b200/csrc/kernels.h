@@ -68,8 +68,15 @@ bool gemm_tc5_supported(const Q4Weight &w, int M);
 size_t gemm_tc5_split_elems(int M, int K);  // bf16 elements needed for the split buffer
 void launch_split_tiles(const float *x, int M, int K, const float *gamma, const float *ada, float eps, void *xt,
                         cudaStream_t st);
+// Caller-owned scratch for the GEMM's deterministic split-K (used when N/128 x M/128 tiles cannot fill the GPU)
+struct GemmWork {
+    float *partial = nullptr;  // [slices][tiles][128][128]
+    size_t partial_floats = 0;
+    int *counters = nullptr;   // [n_counters] zero between launches
+    int n_counters = 0;
+};
 void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int ldy, const float *bias, const float *res,
-                        int epi, cudaStream_t st);
+                        int epi, const GemmWork *gw, cudaStream_t st);
 // conv2 as implicit GEMM: in [B][T_in][C_in] time-major, W [C_out][3*C_in] (k = tap*C_in + c),
 // stride 2, pad 1, + bias, GELU -> out [B][T_out][C_out].
 void launch_conv2_gemm(const float *in, const float *w, const float *bias, float *out, int B, int T_in,

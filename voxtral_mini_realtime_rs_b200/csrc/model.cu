@@ -441,6 +441,12 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
             for (int K : {c.dec_dim, c.dec_heads * c.dec_head_dim, c.dec_ffn}) e = std::max(e, gemm_tc5_split_elems(std::max(rows_d, max_batch * std::max(s->S4_max, 1)), K / 64 * 64));
             s->xt_elems = e;
             s->xt_buf = s->arena.alloc(e * 2);
+            // split-K scratch of the tcgen05 GEMM: at most 148 (slice, tile) partial tiles in flight
+            s->gemm_work.partial_floats = (size_t)148 * 128 * 128;
+            s->gemm_work.partial = s->arena.alloc_n<float>(s->gemm_work.partial_floats);
+            s->gemm_work.n_counters = 128;
+            s->gemm_work.counters = s->arena.alloc_n<int>(s->gemm_work.n_counters);
+            CUDA_OK(cudaMemset(s->gemm_work.counters, 0, sizeof(int) * s->gemm_work.n_counters));
             const char *gv = getenv("VOX_GEMM");
             s->use_gemm_tc = !(gv && std::string(gv) == "simt");
             const char *av = getenv("VOX_ENC_ATTN");
@@ -522,7 +528,7 @@ void Session::linear_n(const Q4Weight &w, const float *x, int M, float *y, int l
                        int epi, const float *gamma, const float *ada, float *tmp) {
     if (M > 8 && use_gemm_tc && gemm_tc5_supported(w, M) && gemm_tc5_split_elems(M, w.K) <= xt_elems) {
         launch_split_tiles(x, M, w.K, gamma, ada, m->norm_eps, xt_buf, st);
-        launch_q4_gemm_tc5(w, xt_buf, M, y, ldy, bias, res, epi, st);
+        launch_q4_gemm_tc5(w, xt_buf, M, y, ldy, bias, res, epi, &gemm_work, st);
         return;
     }
     if (gamma) {
@@ -536,7 +542,7 @@ void Session::linear(const Q4Weight &w, const float *x, int M, float *y, int ldy
                      const float *res, int epi) {
     if (M > 8 && use_gemm_tc && gemm_tc5_supported(w, M) && gemm_tc5_split_elems(M, w.K) <= xt_elems) {
         launch_split_tiles(x, M, w.K, nullptr, nullptr, 0.0f, xt_buf, st);
-        launch_q4_gemm_tc5(w, xt_buf, M, y, ldy, bias, res, epi, st);
+        launch_q4_gemm_tc5(w, xt_buf, M, y, ldy, bias, res, epi, &gemm_work, st);
         return;
     }
     if (M <= 8 && w.qs_tc && use_tc) launch_q4_matvec_tc(w, x, M, y, ldy, bias, res, epi, st);

@@ -143,6 +143,7 @@ struct Session {
     bool fused_decode(int rows) const;
     void *xt_buf = nullptr;   // bf16 split tiles feeding the tcgen05 GEMM
     size_t xt_elems = 0;
+    GemmWork gemm_work;       // split-K scratch of the tcgen05 GEMM
     bool use_enc_attn_tc = true;  // tensor-core encoder attention (VOX_ENC_ATTN=simt disables)
     bool use_gemm_tc = true;  // tcgen05 GEMM for M > 8 (VOX_GEMM=simt disables)
     // y = epi(norm(x) . W^T): RMSNorm fused into the operand split when the tcgen05 path applies,
