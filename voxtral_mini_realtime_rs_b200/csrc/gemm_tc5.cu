@@ -36,8 +36,11 @@ constexpr int G5_BM = 128;   // features per CTA (UMMA M)
 constexpr int G5_BN = 128;   // tokens per CTA (UMMA N)
 constexpr int G5_BK = 64;    // K per pipeline stage
 constexpr int G5_TILE_BYTES = G5_BM * G5_BK * 2;          // 16 KB: one bf16 operand tile
-constexpr int G5_STAGE_BYTES = 5 * G5_TILE_BYTES;         // w_hi, w_lo, x_h, x_m, x_l
-constexpr int G5_STAGES = 2;
+constexpr int G5_STAGES = 2;                              // weight stages (w_hi, w_lo), dequantised in-kernel
+constexpr int G5_XSTAGES = 3;                             // activation stages (x_h, x_m, x_l), fetched one k-step ahead
+constexpr int G5_WSTAGE_BYTES = 2 * G5_TILE_BYTES;
+constexpr int G5_XSTAGE_BYTES = 3 * G5_TILE_BYTES;
+constexpr int G5_SMEM_BYTES = G5_STAGES * G5_WSTAGE_BYTES + G5_XSTAGES * G5_XSTAGE_BYTES;  // 208 KB
 constexpr int G5_TMEM_COLS = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,17 +115,15 @@ struct G5Args {
 template <int EPI>
 __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full_bar[G5_STAGES], done_bar[G5_STAGES];
+    __shared__ __align__(8) uint64_t full_bar[G5_XSTAGES], done_bar[G5_STAGES];
     __shared__ uint32_t tmem_base_smem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int f0 = blockIdx.x * G5_BM, tt = blockIdx.y, tok0 = tt * G5_BN;
     const int bpr = a.K >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < G5_STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&done_bar[s], 1);
-        }
+        for (int s = 0; s < G5_XSTAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < G5_STAGES; ++s) mbar_init(&done_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
@@ -143,40 +144,56 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
     const size_t xt_piece = (size_t)a.TT * a.KC * (G5_TILE_BYTES / 2);  // elements per split piece
 
     const int kc_begin = blockIdx.z * a.KCs, kc_end = min(a.KC, kc_begin + a.KCs);
+    // this thread's Q4 block of the first k-step (rows beyond N: nibble 8 = weight 0, scale 0)
+    uint4 q_cur = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
+    float d_cur = 0.0f;
+    if (gn < a.N && kc_begin < kc_end) {
+        const size_t blk = (size_t)gn * bpr + (size_t)kc_begin * 2 + dblk;
+        q_cur = __ldg(a.qs + blk);
+        d_cur = __half2float(__ldg(a.ds + blk));
+    }
+    unsigned char *xs_base = smem + (size_t)G5_STAGES * G5_WSTAGE_BYTES;
+    auto fetch_x = [&](int kc_f) {  // one thread: the three split pieces of X for k-step kc_f
+        const int xs = (kc_f - kc_begin) % G5_XSTAGES;
+        mbar_expect_tx(&full_bar[xs], 3 * G5_TILE_BYTES);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const __nv_bfloat16 *src = a.xt + p * xt_piece + ((size_t)tt * a.KC + kc_f) * (G5_TILE_BYTES / 2);
+            bulk_g2s(xs_base + (size_t)xs * G5_XSTAGE_BYTES + p * G5_TILE_BYTES, src, G5_TILE_BYTES, &full_bar[xs]);
+        }
+    };
+    if (tid == 0 && kc_begin < kc_end) fetch_x(kc_begin);
     for (int kc = kc_begin; kc < kc_end; ++kc) {
         const int it = kc - kc_begin;
         const int s = it & 1, use = it >> 1;
-        unsigned char *stage = smem + (size_t)s * G5_STAGE_BYTES;
+        unsigned char *stage = smem + (size_t)s * G5_WSTAGE_BYTES;
         if (it >= G5_STAGES) {
-            mbar_wait(&done_bar[s], (uint32_t)((use - 1) & 1));  // MMAs that read this stage have retired
+            mbar_wait(&done_bar[s], (uint32_t)((use - 1) & 1));  // MMAs of k-step it-2 (this W stage, X stage (it+1)%3) retired
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         }
-        if (tid == 0) {
-            mbar_expect_tx(&full_bar[s], 3 * G5_TILE_BYTES);
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                const __nv_bfloat16 *src = a.xt + p * xt_piece + ((size_t)tt * a.KC + kc) * (G5_TILE_BYTES / 2);
-                bulk_g2s(stage + (2 + p) * G5_TILE_BYTES, src, G5_TILE_BYTES, &full_bar[s]);
-            }
-        }
-        // ---- dequantise one Q4 block (32 weights) of row `gn` into the w_hi / w_lo tiles
+        // X of the NEXT k-step goes into the stage k-step it-2 used: its TMA latency hides behind this step
+        if (tid == 0 && kc + 1 < kc_end) fetch_x(kc + 1);
+        // ---- dequantise one Q4 block (32 weights) of row `gn` into the w_hi / w_lo tiles.
+        // The block for this k-step was fetched one iteration ago (q_cur / d_cur); fetch the next one now
+        // so its L2 latency hides behind this step's arithmetic.
         {
-            uint4 q = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
-            float dd = 0.0f;
-            if (gn < a.N) {
-                const size_t blk = (size_t)gn * bpr + (size_t)kc * 2 + dblk;
-                q = __ldg(a.qs + blk);
-                dd = __half2float(__ldg(a.ds + blk));
+            const uint4 q = q_cur;
+            const float dd = d_cur;
+            if (gn < a.N && kc + 1 < kc_end) {
+                const size_t blk = (size_t)gn * bpr + (size_t)(kc + 1) * 2 + dblk;
+                q_cur = __ldg(a.qs + blk);
+                d_cur = __half2float(__ldg(a.ds + blk));
             }
             const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-            float wl[16], wh[16];  // elements 0..15 (low nibbles), 16..31 (high nibbles)
+            // nibble n -> float (n - 8) without an int->float conversion: 0x4B000000 | n = 2^23 + n
+            float wl[16], wh[16];  // elements 0..15 (low nibbles), 16..31 (high nibbles), times the block scale
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi)
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const uint32_t byte = (w4[wi] >> (8 * t)) & 0xFFu;
-                    wl[wi * 4 + t] = ((float)(byte & 0xFu) - 8.0f) * dd;
-                    wh[wi * 4 + t] = ((float)(byte >> 4) - 8.0f) * dd;
+                    const uint32_t lo_n = (w4[wi] >> (8 * t)) & 0xFu, hi_n = (w4[wi] >> (8 * t + 4)) & 0xFu;
+                    wl[wi * 4 + t] = (__uint_as_float(0x4B000000u | lo_n) - 8388616.0f) * dd;
+                    wh[wi * 4 + t] = (__uint_as_float(0x4B000000u | hi_n) - 8388616.0f) * dd;
                 }
             // tile layout: [8 k-chunks of 8 elements][128 rows][16 bytes]
             unsigned char *thi = stage, *tlo = stage + G5_TILE_BYTES;
@@ -187,11 +204,12 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float v0 = src[2 * e], v1 = src[2 * e + 1];
-                    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-                    const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-                    const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-                    ph[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    pl[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);  // one packed conversion per pair
+                    const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2);
+                    const float r0 = v0 - __uint_as_float(hb << 16), r1 = v1 - __uint_as_float(hb & 0xFFFF0000u);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+                    ph[e] = hb;
+                    pl[e] = *reinterpret_cast<const uint32_t *>(&l2);
                 }
                 const int off = (dblk * 4 + c) * (G5_BM * 16) + drow * 16;
                 *reinterpret_cast<uint4 *>(thi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -201,18 +219,20 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes -> async (UMMA) reads
         __syncthreads();
         if (tid == 0) {
-            mbar_wait(&full_bar[s], (uint32_t)(use & 1));
+            const int xs = it % G5_XSTAGES;
+            mbar_wait(&full_bar[xs], (uint32_t)((it / G5_XSTAGES) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t base = smem_u32(stage);
+            const uint32_t xbase = smem_u32(xs_base + (size_t)xs * G5_XSTAGE_BYTES);
             const uint32_t lbo = G5_BM * 16, sbo = 128;  // K-chunk stride, 8-row group stride
 #pragma unroll
             for (int ks = 0; ks < G5_BK / 16; ++ks) {
                 const uint32_t koff = (uint32_t)ks * 2u * lbo;
                 const uint64_t whi = umma_desc(base + 0 * G5_TILE_BYTES + koff, lbo, sbo);
                 const uint64_t wlo = umma_desc(base + 1 * G5_TILE_BYTES + koff, lbo, sbo);
-                const uint64_t xh = umma_desc(base + 2 * G5_TILE_BYTES + koff, lbo, sbo);
-                const uint64_t xm = umma_desc(base + 3 * G5_TILE_BYTES + koff, lbo, sbo);
-                const uint64_t xl = umma_desc(base + 4 * G5_TILE_BYTES + koff, lbo, sbo);
+                const uint64_t xh = umma_desc(xbase + 0 * G5_TILE_BYTES + koff, lbo, sbo);
+                const uint64_t xm = umma_desc(xbase + 1 * G5_TILE_BYTES + koff, lbo, sbo);
+                const uint64_t xl = umma_desc(xbase + 2 * G5_TILE_BYTES + koff, lbo, sbo);
                 // smallest terms first
                 umma_bf16(tmem_d, wlo, xm, idesc, (it | ks) != 0);
                 umma_bf16(tmem_d, whi, xl, idesc, 1);
@@ -427,7 +447,7 @@ void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int 
     a.ldy = ldy;
     a.bias = bias;
     a.res = res;
-    const size_t smem = (size_t)G5_STAGES * G5_STAGE_BYTES + 1024;
+    const size_t smem = (size_t)G5_SMEM_BYTES + 1024;
     // split K when the output tiles alone cannot fill the GPU (single-stream encode: N = 1280 -> 50 tiles;
     // prefill: 38 tokens -> one token tile)
     const int tiles = (w.N / G5_BM) * a.TT;
