@@ -27,4 +27,12 @@ timeout 600 ncu --profile-from-start off --set full --clock-control none --impor
   -k regex:gemm_tc5 -s 4 -c 3 -o gpurun_out/gemm_tc5_${TAG} \
   python scripts/profile_decode.py --region encode --streams 8 >> gpurun_out/profile_${TAG}.log 2>&1
 echo "ncu gemm exit $?"
+# the persistent decode-step kernel (B = 8: the roofline launch of bench.py)
+timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
+  -k regex:decode_mega -s 20 -c 1 -o gpurun_out/mega_${TAG}_b8 \
+  python scripts/profile_decode.py --streams 8 >> gpurun_out/profile_${TAG}.log 2>&1
+echo "ncu mega exit $?"
+timeout 300 python scripts/mega_trace.py --streams 8 > gpurun_out/mega_trace_${TAG}_b8.txt 2>&1
+timeout 300 python scripts/mega_trace.py --streams 1 > gpurun_out/mega_trace_${TAG}_b1.txt 2>&1
+tail -12 gpurun_out/mega_trace_${TAG}_b8.txt
 ls -la gpurun_out | tail -12

@@ -31,7 +31,9 @@ void tc_count_launch(const char *name);
 
 namespace {
 
-constexpr int G5_THREADS = 256;
+constexpr int G5_DQ_WARPS = 16;                           // dequantising warps (also the epilogue warps)
+constexpr int G5_DQ_THREADS = G5_DQ_WARPS * 32;
+constexpr int G5_THREADS = G5_DQ_THREADS + 32;            // + the control warp (TMA + MMA issue)
 constexpr int G5_BM = 128;   // features per CTA (UMMA M)
 constexpr int G5_BN = 128;   // tokens per CTA (UMMA N)
 constexpr int G5_BK = 64;    // K per pipeline stage
@@ -49,6 +51,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
@@ -115,7 +120,7 @@ struct G5Args {
 template <int EPI>
 __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full_bar[G5_XSTAGES], done_bar[G5_STAGES];
+    __shared__ __align__(8) uint64_t full_bar[G5_XSTAGES], wfull_bar[G5_STAGES], done_bar[G5_STAGES];
     __shared__ uint32_t tmem_base_smem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int f0 = blockIdx.x * G5_BM, tt = blockIdx.y, tok0 = tt * G5_BN;
@@ -123,7 +128,10 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
 
     if (tid == 0) {
         for (int s = 0; s < G5_XSTAGES; ++s) mbar_init(&full_bar[s], 1);
-        for (int s = 0; s < G5_STAGES; ++s) mbar_init(&done_bar[s], 1);
+        for (int s = 0; s < G5_STAGES; ++s) {
+            mbar_init(&wfull_bar[s], G5_DQ_WARPS);  // one arrival per dequantising warp
+            mbar_init(&done_bar[s], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
@@ -137,110 +145,112 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_d = tmem_base_smem;
     const uint32_t idesc = umma_idesc_bf16(G5_BM, G5_BN);
-
-    // dequant mapping: thread -> (feature row, block within the 64-wide chunk)
-    const int drow = tid >> 1, dblk = tid & 1;
-    const int gn = f0 + drow;
     const size_t xt_piece = (size_t)a.TT * a.KC * (G5_TILE_BYTES / 2);  // elements per split piece
-
     const int kc_begin = blockIdx.z * a.KCs, kc_end = min(a.KC, kc_begin + a.KCs);
-    // this thread's Q4 block of the first k-step (rows beyond N: nibble 8 = weight 0, scale 0)
-    uint4 q_cur = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
-    float d_cur = 0.0f;
-    if (gn < a.N && kc_begin < kc_end) {
-        const size_t blk = (size_t)gn * bpr + (size_t)kc_begin * 2 + dblk;
-        q_cur = __ldg(a.qs + blk);
-        d_cur = __half2float(__ldg(a.ds + blk));
-    }
     unsigned char *xs_base = smem + (size_t)G5_STAGES * G5_WSTAGE_BYTES;
-    auto fetch_x = [&](int kc_f) {  // one thread: the three split pieces of X for k-step kc_f
-        const int xs = (kc_f - kc_begin) % G5_XSTAGES;
-        mbar_expect_tx(&full_bar[xs], 3 * G5_TILE_BYTES);
+
+    if (warp == G5_DQ_WARPS) {
+        // =========== control warp: X tiles by TMA one k-step ahead, MMA issue as soon as W and X are in ===========
+        if (lane == 0) {
+            auto fetch_x = [&](int kc_f) {  // the three split pieces of X for k-step kc_f
+                const int xs = (kc_f - kc_begin) % G5_XSTAGES;
+                mbar_expect_tx(&full_bar[xs], 3 * G5_TILE_BYTES);
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {
-            const __nv_bfloat16 *src = a.xt + p * xt_piece + ((size_t)tt * a.KC + kc_f) * (G5_TILE_BYTES / 2);
-            bulk_g2s(xs_base + (size_t)xs * G5_XSTAGE_BYTES + p * G5_TILE_BYTES, src, G5_TILE_BYTES, &full_bar[xs]);
+                for (int p = 0; p < 3; ++p) {
+                    const __nv_bfloat16 *src = a.xt + p * xt_piece + ((size_t)tt * a.KC + kc_f) * (G5_TILE_BYTES / 2);
+                    bulk_g2s(xs_base + (size_t)xs * G5_XSTAGE_BYTES + p * G5_TILE_BYTES, src, G5_TILE_BYTES, &full_bar[xs]);
+                }
+            };
+            if (kc_begin < kc_end) fetch_x(kc_begin);
+            for (int kc = kc_begin; kc < kc_end; ++kc) {
+                const int it = kc - kc_begin;
+                const int s = it & 1, use = it >> 1, xs = it % G5_XSTAGES;
+                if (it >= G5_STAGES) mbar_wait(&done_bar[s], (uint32_t)((use - 1) & 1));  // k-step it-2 retired: its X stage is free
+                if (kc + 1 < kc_end) fetch_x(kc + 1);
+                mbar_wait(&wfull_bar[s], (uint32_t)(use & 1));                 // W tiles of this k-step dequantised
+                mbar_wait(&full_bar[xs], (uint32_t)((it / G5_XSTAGES) & 1));   // X tiles landed
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint32_t base = smem_u32(smem + (size_t)s * G5_WSTAGE_BYTES);
+                const uint32_t xbase = smem_u32(xs_base + (size_t)xs * G5_XSTAGE_BYTES);
+                const uint32_t lbo = G5_BM * 16, sbo = 128;  // K-chunk stride, 8-row group stride
+#pragma unroll
+                for (int ks = 0; ks < G5_BK / 16; ++ks) {
+                    const uint32_t koff = (uint32_t)ks * 2u * lbo;
+                    const uint64_t whi = umma_desc(base + 0 * G5_TILE_BYTES + koff, lbo, sbo);
+                    const uint64_t wlo = umma_desc(base + 1 * G5_TILE_BYTES + koff, lbo, sbo);
+                    const uint64_t xh = umma_desc(xbase + 0 * G5_TILE_BYTES + koff, lbo, sbo);
+                    const uint64_t xm = umma_desc(xbase + 1 * G5_TILE_BYTES + koff, lbo, sbo);
+                    const uint64_t xl = umma_desc(xbase + 2 * G5_TILE_BYTES + koff, lbo, sbo);
+                    // smallest terms first
+                    umma_bf16(tmem_d, wlo, xm, idesc, (it | ks) != 0);
+                    umma_bf16(tmem_d, whi, xl, idesc, 1);
+                    umma_bf16(tmem_d, wlo, xh, idesc, 1);
+                    umma_bf16(tmem_d, whi, xm, idesc, 1);
+                    umma_bf16(tmem_d, whi, xh, idesc, 1);
+                }
+                umma_commit(&done_bar[s]);
+            }
         }
-    };
-    if (tid == 0 && kc_begin < kc_end) fetch_x(kc_begin);
-    for (int kc = kc_begin; kc < kc_end; ++kc) {
-        const int it = kc - kc_begin;
-        const int s = it & 1, use = it >> 1;
-        unsigned char *stage = smem + (size_t)s * G5_WSTAGE_BYTES;
-        if (it >= G5_STAGES) {
-            mbar_wait(&done_bar[s], (uint32_t)((use - 1) & 1));  // MMAs of k-step it-2 (this W stage, X stage (it+1)%3) retired
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    } else {
+        // =========== dequantising warps: thread -> (feature row, Q4 block of the 64-wide chunk, nibble half) ===========
+        const int drow = tid >> 2, dblk = (tid >> 1) & 1, dhalf = tid & 1;
+        const int gn = f0 + drow;
+        // this thread's Q4 block of the first k-step (rows beyond N: nibble 8 = weight 0, scale 0)
+        uint4 q_cur = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
+        float d_cur = 0.0f;
+        if (gn < a.N && kc_begin < kc_end) {
+            const size_t blk = (size_t)gn * bpr + (size_t)kc_begin * 2 + dblk;
+            q_cur = __ldg(a.qs + blk);
+            d_cur = __half2float(__ldg(a.ds + blk));
         }
-        // X of the NEXT k-step goes into the stage k-step it-2 used: its TMA latency hides behind this step
-        if (tid == 0 && kc + 1 < kc_end) fetch_x(kc + 1);
-        // ---- dequantise one Q4 block (32 weights) of row `gn` into the w_hi / w_lo tiles.
-        // The block for this k-step was fetched one iteration ago (q_cur / d_cur); fetch the next one now
-        // so its L2 latency hides behind this step's arithmetic.
-        {
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
+            const int it = kc - kc_begin;
+            const int s = it & 1, use = it >> 1;
+            unsigned char *stage = smem + (size_t)s * G5_WSTAGE_BYTES;
             const uint4 q = q_cur;
             const float dd = d_cur;
-            if (gn < a.N && kc + 1 < kc_end) {
+            if (gn < a.N && kc + 1 < kc_end) {  // next k-step's block: its L2 latency hides behind this step
                 const size_t blk = (size_t)gn * bpr + (size_t)(kc + 1) * 2 + dblk;
                 q_cur = __ldg(a.qs + blk);
                 d_cur = __half2float(__ldg(a.ds + blk));
             }
-            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+            // 16 weights of the block: low nibbles (elements 0..15, dhalf = 0) or high nibbles (16..31), times d.
             // nibble n -> float (n - 8) without an int->float conversion: 0x4B000000 | n = 2^23 + n
-            float wl[16], wh[16];  // elements 0..15 (low nibbles), 16..31 (high nibbles), times the block scale
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+            float wv[16];
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi)
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const uint32_t lo_n = (w4[wi] >> (8 * t)) & 0xFu, hi_n = (w4[wi] >> (8 * t + 4)) & 0xFu;
-                    wl[wi * 4 + t] = (__uint_as_float(0x4B000000u | lo_n) - 8388616.0f) * dd;
-                    wh[wi * 4 + t] = (__uint_as_float(0x4B000000u | hi_n) - 8388616.0f) * dd;
+                    const uint32_t n = (w4[wi] >> (8 * t + 4 * dhalf)) & 0xFu;
+                    wv[wi * 4 + t] = (__uint_as_float(0x4B000000u | n) - 8388616.0f) * dd;
                 }
-            // tile layout: [8 k-chunks of 8 elements][128 rows][16 bytes]
+            uint32_t ph[8], pl[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float v0 = wv[2 * e], v1 = wv[2 * e + 1];
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);  // one packed conversion per pair
+                const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2);
+                const float r0 = v0 - __uint_as_float(hb << 16), r1 = v1 - __uint_as_float(hb & 0xFFFF0000u);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+                ph[e] = hb;
+                pl[e] = *reinterpret_cast<const uint32_t *>(&l2);
+            }
+            if (it >= G5_STAGES) {
+                mbar_wait(&done_bar[s], (uint32_t)((use - 1) & 1));  // MMAs that read this W stage have retired
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            }
+            // tile layout: [8 k-chunks of 8 elements][128 rows][16 bytes]; this thread owns k-chunks dblk*4 + dhalf*2 + {0,1}
             unsigned char *thi = stage, *tlo = stage + G5_TILE_BYTES;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {  // this block covers k-chunks dblk*4 + c
-                const float *src = (c < 2) ? (wl + c * 8) : (wh + (c - 2) * 8);
-                uint32_t ph[4], pl[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float v0 = src[2 * e], v1 = src[2 * e + 1];
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);  // one packed conversion per pair
-                    const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2);
-                    const float r0 = v0 - __uint_as_float(hb << 16), r1 = v1 - __uint_as_float(hb & 0xFFFF0000u);
-                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
-                    ph[e] = hb;
-                    pl[e] = *reinterpret_cast<const uint32_t *>(&l2);
-                }
-                const int off = (dblk * 4 + c) * (G5_BM * 16) + drow * 16;
-                *reinterpret_cast<uint4 *>(thi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                *reinterpret_cast<uint4 *>(tlo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            for (int c = 0; c < 2; ++c) {
+                const int off = (dblk * 4 + dhalf * 2 + c) * (G5_BM * 16) + drow * 16;
+                *reinterpret_cast<uint4 *>(thi + off) = make_uint4(ph[4 * c + 0], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
+                *reinterpret_cast<uint4 *>(tlo + off) = make_uint4(pl[4 * c + 0], pl[4 * c + 1], pl[4 * c + 2], pl[4 * c + 3]);
             }
-        }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes -> async (UMMA) reads
-        __syncthreads();
-        if (tid == 0) {
-            const int xs = it % G5_XSTAGES;
-            mbar_wait(&full_bar[xs], (uint32_t)((it / G5_XSTAGES) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint32_t base = smem_u32(stage);
-            const uint32_t xbase = smem_u32(xs_base + (size_t)xs * G5_XSTAGE_BYTES);
-            const uint32_t lbo = G5_BM * 16, sbo = 128;  // K-chunk stride, 8-row group stride
-#pragma unroll
-            for (int ks = 0; ks < G5_BK / 16; ++ks) {
-                const uint32_t koff = (uint32_t)ks * 2u * lbo;
-                const uint64_t whi = umma_desc(base + 0 * G5_TILE_BYTES + koff, lbo, sbo);
-                const uint64_t wlo = umma_desc(base + 1 * G5_TILE_BYTES + koff, lbo, sbo);
-                const uint64_t xh = umma_desc(xbase + 0 * G5_TILE_BYTES + koff, lbo, sbo);
-                const uint64_t xm = umma_desc(xbase + 1 * G5_TILE_BYTES + koff, lbo, sbo);
-                const uint64_t xl = umma_desc(xbase + 2 * G5_TILE_BYTES + koff, lbo, sbo);
-                // smallest terms first
-                umma_bf16(tmem_d, wlo, xm, idesc, (it | ks) != 0);
-                umma_bf16(tmem_d, whi, xl, idesc, 1);
-                umma_bf16(tmem_d, wlo, xh, idesc, 1);
-                umma_bf16(tmem_d, whi, xm, idesc, 1);
-                umma_bf16(tmem_d, whi, xh, idesc, 1);
-            }
-            umma_commit(&done_bar[s]);
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes -> async (UMMA) reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&wfull_bar[s]);
         }
     }
     // ---- wait for the last commit of each stage (covers every MMA issued before it)
@@ -252,37 +262,34 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
         }
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     }
-    // ---- epilogue: warp w reads TMEM lanes 32*(w%4).. (features), columns 64*(w/4).. (tokens)
+    // ---- epilogue: dequant warp w reads TMEM lanes 32*(w%4).. (features), columns 32*(w/4).. (tokens)
     {
         __shared__ int is_last;
-        const int q4 = warp & 3, hcol = warp >> 2;
+        const bool ew = warp < G5_DQ_WARPS;  // the control warp only joins the barriers
+        const int q4 = warp & 3, col0 = (warp >> 2) * 32;
         const int feat = f0 + q4 * 32 + lane;
         const int tile_id = blockIdx.y * gridDim.x + blockIdx.x, n_tile = gridDim.x * gridDim.y;
         float *ptile = a.SK > 1 ? a.partial + ((size_t)blockIdx.z * n_tile + tile_id) * (G5_BM * G5_BN) : nullptr;
-        uint32_t r[2][32];
-#pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
-            const int col0 = hcol * 64 + cb * 32;
+        uint32_t r[32];
+        if (ew) {
             const uint32_t taddr = tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-                : "=r"(r[cb][0]), "=r"(r[cb][1]), "=r"(r[cb][2]), "=r"(r[cb][3]), "=r"(r[cb][4]), "=r"(r[cb][5]), "=r"(r[cb][6]),
-                  "=r"(r[cb][7]), "=r"(r[cb][8]), "=r"(r[cb][9]), "=r"(r[cb][10]), "=r"(r[cb][11]), "=r"(r[cb][12]), "=r"(r[cb][13]),
-                  "=r"(r[cb][14]), "=r"(r[cb][15]), "=r"(r[cb][16]), "=r"(r[cb][17]), "=r"(r[cb][18]), "=r"(r[cb][19]), "=r"(r[cb][20]),
-                  "=r"(r[cb][21]), "=r"(r[cb][22]), "=r"(r[cb][23]), "=r"(r[cb][24]), "=r"(r[cb][25]), "=r"(r[cb][26]), "=r"(r[cb][27]),
-                  "=r"(r[cb][28]), "=r"(r[cb][29]), "=r"(r[cb][30]), "=r"(r[cb][31])
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
         }
         bool run_epilogue = true;
         if (a.SK > 1) {
             // publish this slice's tile, take a ticket; the last arriver sums the slices in order
+            if (ew) {
 #pragma unroll
-            for (int cb = 0; cb < 2; ++cb)
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    __stcg(ptile + (size_t)(hcol * 64 + cb * 32 + j) * G5_BM + q4 * 32 + lane, __uint_as_float(r[cb][j]));
+                for (int j = 0; j < 32; ++j) __stcg(ptile + (size_t)(col0 + j) * G5_BM + q4 * 32 + lane, __uint_as_float(r[j]));
+            }
             __syncthreads();
             if (tid == 0) {
                 __threadfence();
@@ -296,39 +303,32 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
             }
             __syncthreads();
             run_epilogue = is_last != 0;
-            if (run_epilogue) {
-#pragma unroll
-                for (int cb = 0; cb < 2; ++cb)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float v = 0.0f;
-                        for (int z = 0; z < a.SK; ++z)
-                            v += __ldcg(a.partial + ((size_t)z * n_tile + tile_id) * (G5_BM * G5_BN) +
-                                        (size_t)(hcol * 64 + cb * 32 + j) * G5_BM + q4 * 32 + lane);
-                        r[cb][j] = __float_as_uint(v);
-                    }
-            }
-        }
-        if (run_epilogue) {
-            const float bsv = (a.bias && feat < a.N) ? a.bias[feat] : 0.0f;
-#pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-                const int col0 = hcol * 64 + cb * 32;
+            if (run_epilogue && ew) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int tok = tok0 + col0 + j;
-                    float v = __uint_as_float(r[cb][j]);
-                    if (EPI == EPI_SILU_MUL) {
-                        // features (2i, 2i+1) = (gate, up) sit in adjacent lanes
-                        const float other = __shfl_xor_sync(0xffffffffu, v, 1);
-                        if ((lane & 1) == 0 && tok < a.M && feat + 1 < a.N)
-                            a.y[(size_t)tok * a.ldy + (feat >> 1)] = (v / (1.0f + expf(-v))) * other;
-                    } else if (tok < a.M && feat < a.N) {
-                        v += bsv;
-                        if (EPI == EPI_RESIDUAL) v += a.res[(size_t)tok * a.ldy + feat];
-                        if (EPI == EPI_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-                        a.y[(size_t)tok * a.ldy + feat] = v;
-                    }
+                    float v = 0.0f;
+                    for (int z = 0; z < a.SK; ++z)
+                        v += __ldcg(a.partial + ((size_t)z * n_tile + tile_id) * (G5_BM * G5_BN) + (size_t)(col0 + j) * G5_BM + q4 * 32 + lane);
+                    r[j] = __float_as_uint(v);
+                }
+            }
+        }
+        if (run_epilogue && ew) {
+            const float bsv = (a.bias && feat < a.N) ? a.bias[feat] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int tok = tok0 + col0 + j;
+                float v = __uint_as_float(r[j]);
+                if (EPI == EPI_SILU_MUL) {
+                    // features (2i, 2i+1) = (gate, up) sit in adjacent lanes
+                    const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+                    if ((lane & 1) == 0 && tok < a.M && feat + 1 < a.N)
+                        a.y[(size_t)tok * a.ldy + (feat >> 1)] = (v / (1.0f + expf(-v))) * other;
+                } else if (tok < a.M && feat < a.N) {
+                    v += bsv;
+                    if (EPI == EPI_RESIDUAL) v += a.res[(size_t)tok * a.ldy + feat];
+                    if (EPI == EPI_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+                    a.y[(size_t)tok * a.ldy + feat] = v;
                 }
             }
         }
