@@ -37,7 +37,8 @@ def main():
         return
     tr = tr.reshape(-1, 6)
     n = tr.shape[0]
-    names = ["embed"] + ["qkv", "attn", "amerge", "wo", "w13", "w2"] * ((n - 3) // 6) + ["lm_head", "argmax"]
+    per_layer = ["qkv", "attn", "wo", "w13", "w2"]
+    names = ["embed"] + per_layer * ((n - 3) // len(per_layer)) + ["lm_head", "argmax"]
     agg = {}
     for i, nm in enumerate(names):
         t0, t1, t2, t3, t4, t5 = tr[i]

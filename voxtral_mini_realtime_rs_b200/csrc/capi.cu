@@ -61,6 +61,7 @@ struct vox_q4 {
     TcWork wk;  // split-K scratch of the tensor-core matvec (allocated with the tensor)
     void *xt = nullptr;  // split tiles for the tcgen05 GEMM (M > 8)
     size_t xt_elems = 0;
+    GemmWork gw;  // split-K scratch of the tcgen05 GEMM (allocated on first use)
 };
 struct vox_model { Model *m; };
 struct vox_session { Session *s; };
@@ -327,8 +328,15 @@ static void q4_matmul_dispatch(const Q4Weight &w, const float *x, float *y, int 
             h->xt = h->arena.alloc(need * 2);
             h->xt_elems = need;
         }
+        if (!h->gw.partial) {
+            h->gw.partial_floats = (size_t)148 * 128 * 128;
+            h->gw.partial = h->arena.alloc_n<float>(h->gw.partial_floats);
+            h->gw.n_counters = 128;
+            h->gw.counters = h->arena.alloc_n<int>(h->gw.n_counters);
+            CUDA_OK(cudaMemset(h->gw.counters, 0, sizeof(int) * h->gw.n_counters));
+        }
         launch_split_tiles(x, rows, w.K, nullptr, nullptr, 0.0f, h->xt, st);
-        launch_q4_gemm_tc5(w, h->xt, rows, y, w.N, bias, nullptr, EPI_NONE, nullptr, st);
+        launch_q4_gemm_tc5(w, h->xt, rows, y, w.N, bias, nullptr, EPI_NONE, &h->gw, st);
         return;
     }
     if (rows <= 8 && w.qs_tc && !simt)

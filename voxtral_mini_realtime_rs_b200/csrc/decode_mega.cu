@@ -119,6 +119,14 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_release_s32(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_s32(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void red_release_add(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
@@ -168,6 +176,10 @@ __device__ __forceinline__ int mg_tile_count(const int n_tiles, const int UT, co
 __device__ __forceinline__ int mg_tile_of(const int i, const int UT, const int cta, const int nctas) {
     return (cta + (i / UT) * nctas) * UT + (i % UT);
 }
+// exp for the decoder attention's softmax: ex2.approx(x * log2 e) (2 instructions; the full-range expf is ~25 and
+// made a one-key-per-warp KV walk cost 3.3 us).  Relative error <= ~|x| * 2^-23: far below the 1e-3 parity bound,
+// and the reference's own softmax runs WGSL exp on the GPU.
+__device__ __forceinline__ float fast_exp(const float x) { return __expf(x); }
 __device__ __forceinline__ void amax_combine(float &bv, int &bx, const float ov, const int ox) {
     if (ov > bv || (ov == bv && ox < bx)) { bv = ov; bx = ox; }
 }
@@ -230,6 +242,7 @@ template <int MT, int G, int DPL>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaParams p) {
     constexpr int CG = (MT + 3) / 4;
     constexpr int HD = DPL * 32;
+    static_assert(G * HD <= MG_CTHREADS, "one attention output per consumer thread");
     constexpr int NT = mg_nt(MT);
     constexpr int RW = (NT * 16 * MT + 31) / 32;  // warps that add the per-warp partial sums and run the epilogue
     extern __shared__ __align__(128) unsigned char smem[];
@@ -318,6 +331,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     // =========================== consumers ===========================
     const int pos = *p.d_pos;
     const int outpos = *p.d_outpos;
+    const int epoch = *p.d_epoch;  // decode steps run by this session so far (attention chunk flags)
     int stage = 0;
     uint32_t phase = 0, stg_phase = 0;
     int par = 0;
@@ -341,6 +355,25 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             prefetch_l1(reinterpret_cast<const unsigned char *>(&p.ops[oi + 1]) + 128);
         }
         if (kind == MG_MATVEC) {
+            if (tid == 0 && oi + 1 < p.n_ops && !(p.flags & 2)) {
+                // the next phase is this layer's attention: pull this CTA's chunk of the KV cache into L2 now, so the
+                // walk does not wait on DRAM behind the weight stream
+                const MegaOp &nx = p.ops[oi + 1];
+                if (nx.kind == MG_ATTN && pos < p.max_seq) {
+                    const int NC = p.attn_chunks;
+                    const int j_lo = pos - p.window > 0 ? pos - p.window : 0;
+                    const int per = (pos - j_lo + NC) / NC;
+                    for (int unit = cta; unit < B * p.Hkv * NC; unit += nctas) {
+                        const int ch = unit % NC, bk = unit / NC;
+                        const int j0 = j_lo + ch * per, j1 = min(pos, j0 + per);  // row `pos` is not written yet
+                        if (j1 > j0) {
+                            const size_t off = ((size_t)bk * p.max_seq + j0) * HD;
+                            bulk_prefetch_l2(nx.kc + off, (uint32_t)(j1 - j0) * HD * 4u);
+                            bulk_prefetch_l2(nx.vc + off, (uint32_t)(j1 - j0) * HD * 4u);
+                        }
+                    }
+                }
+            }
             const int n_tiles = op.n_tiles, n_pairs = op.n_pairs, S = op.S, Ps = op.Ps, N = op.N, K = op.K;
             const int epi = op.epi, ldy = op.ldy, track = op.track_argmax, UT = op.unit_tiles;
             const bool has_norm = op.gamma != nullptr;
@@ -710,11 +743,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                             sc[u][h] = (jb + u * MG_CWARPS < j1) ? sc[u][h] * p.scale : -INFINITY;
                             m_new = fmaxf(m_new, sc[u][h]);
                         }
-                        const float alpha = expf(m_run[h] - m_new);  // exp(-inf) = 0 on the first batch
+                        const float alpha = fast_exp(m_run[h] - m_new);  // exp(-inf) = 0 on the first batch
                         float pe[KU], ps = 0.0f;
 #pragma unroll
                         for (int u = 0; u < KU; ++u) {
-                            pe[u] = expf(sc[u][h] - m_new);  // masked keys: exp(-inf) = 0
+                            pe[u] = fast_exp(sc[u][h] - m_new);  // masked keys: exp(-inf) = 0
                             ps += pe[u];
                         }
                         l_run[h] = l_run[h] * alpha + ps;
@@ -739,7 +772,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                     for (int i = 0; i < DPL; ++i) red_acc[((size_t)warp * G + h) * HD + lane * DPL + i] = acc[h][i];
                 }
                 cbar();
-                // the unit's softmax state (max, sum, unnormalised weighted V) for the merge phase
+                // ---- combine the warps; with several key chunks per (stream, kv head) the last chunk's CTA also
+                // combines the chunks (pairwise release/acquire flags: no grid-wide phase for the merge)
+                const int u0 = bk * NC;
+                const int target = epoch * 64 + op.layer + 1;  // unique per (decode step, layer), monotonic
+                float o_final = 0.0f;                           // thread i < G*HD: output (head i / HD, dim i % HD)
                 for (int i = tid; i < G * HD; i += MG_CTHREADS) {
                     const int h = i / HD, d = i - h * HD;
                     float mx = -INFINITY;
@@ -749,64 +786,82 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
 #pragma unroll
                     for (int w = 0; w < MG_CWARPS; ++w) {
                         const float mw = red_m[w * G + h];
-                        const float f = (mw == -INFINITY) ? 0.0f : expf(mw - mx);
+                        const float f = (mw == -INFINITY) ? 0.0f : fast_exp(mw - mx);
                         num = fmaf(red_acc[((size_t)w * G + h) * HD + d], f, num);
                         den = fmaf(red_l[w * G + h], f, den);
                     }
-                    p.att_acc[((size_t)unit * G + h) * HD + d] = num;
-                    if (d == 0) {
-                        p.att_ml[((size_t)unit * G + h) * 2 + 0] = mx;
-                        p.att_ml[((size_t)unit * G + h) * 2 + 1] = den;
+                    if (NC > 1) {
+                        p.att_acc[((size_t)unit * G + h) * HD + d] = num;
+                        if (d == 0) {
+                            p.att_ml[((size_t)unit * G + h) * 2 + 0] = mx;
+                            p.att_ml[((size_t)unit * G + h) * 2 + 1] = den;
+                        }
+                    } else {
+                        o_final = num / den;
                     }
                 }
-            }
-        } else if (kind == MG_ATTN_MERGE) {
-            // attn[b][head][d] = sum_c acc_c e^(m_c - M) / sum_c l_c e^(m_c - M) over the key chunks, in chunk order
-            const int H = p.H, Hkv = p.Hkv, NC = p.attn_chunks;
-            const int total = B * H * HD;
-            for (int e = cta * MG_CTHREADS + tid; e < total && pos < p.max_seq; e += nctas * MG_CTHREADS) {
-                const int d = e % HD, hh = (e / HD) % H, b = e / (HD * H);
-                const int kvh = hh / G, h = hh - kvh * G;
-                const size_t u0 = ((size_t)b * Hkv + kvh) * NC;
-                float mc[16], lc[16], ac[16];
+                if (NC > 1) {
+                    cbar();  // the CTA's chunk state is written
+                    if (tid == 0) {
+                        __threadfence();
+                        st_release_s32(p.att_flags + unit, target);
+                    }
+                    if (ch != NC - 1) continue;  // only the last chunk's CTA goes on to merge
+                    if (tid < NC - 1) {
+                        const long long t0 = clock64();
+                        unsigned n = 0;
+                        while (ld_acquire_s32(p.att_flags + u0 + tid) < target) {
+                            if ((++n & 0x3FFu) == 0 && clock64() - t0 > MG_SPIN_CYCLES) mg_die(wd_flag, 0x600u + (unsigned)oi);
+                        }
+                    }
+                    cbar();
+                    for (int i = tid; i < G * HD; i += MG_CTHREADS) {
+                        const int h = i / HD, d = i - h * HD;
+                        float mc[16], lc[16], ac[16];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {  // all loads first (in-order issue: a use would serialise them)
-                    mc[c] = -INFINITY;
-                    lc[c] = 0.0f;
-                    ac[c] = 0.0f;
-                    if (c < NC) {
-                        mc[c] = __ldcg(p.att_ml + ((u0 + c) * G + h) * 2 + 0);
-                        lc[c] = __ldcg(p.att_ml + ((u0 + c) * G + h) * 2 + 1);
-                        ac[c] = __ldcg(p.att_acc + ((u0 + c) * G + h) * HD + d);
+                        for (int c = 0; c < 16; ++c) {  // all loads first (in-order issue: a use would serialise them)
+                            mc[c] = -INFINITY;
+                            lc[c] = 0.0f;
+                            ac[c] = 0.0f;
+                            if (c < NC) {
+                                mc[c] = __ldcg(p.att_ml + ((size_t)(u0 + c) * G + h) * 2 + 0);
+                                lc[c] = __ldcg(p.att_ml + ((size_t)(u0 + c) * G + h) * 2 + 1);
+                                ac[c] = __ldcg(p.att_acc + ((size_t)(u0 + c) * G + h) * HD + d);
+                            }
+                        }
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) mx = fmaxf(mx, mc[c]);
+                        float num = 0.0f, den = 0.0f;
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            if (c < NC) {
+                                const float f = (mc[c] == -INFINITY) ? 0.0f : fast_exp(mc[c] - mx);
+                                num = fmaf(ac[c], f, num);
+                                den = fmaf(lc[c], f, den);
+                            }
+                        }
+                        o_final = num / den;
                     }
                 }
-                float mx = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 16; ++c) mx = fmaxf(mx, mc[c]);
-                float num = 0.0f, den = 0.0f;
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    if (c < NC) {
-                        const float f = (mc[c] == -INFINITY) ? 0.0f : expf(mc[c] - mx);
-                        num = fmaf(ac[c], f, num);
-                        den = fmaf(lc[c], f, den);
-                    }
+                // ---- attention output + its fragments for wo: a warp holds 32 consecutive dims of one head = one block
+                if (tid < ((G * HD + 31) / 32) * 32) {
+                    const bool oact = tid < G * HD;
+                    const int h = tid / HD, d = tid - h * HD;
+                    if (oact) p.attn_out[(size_t)b * (H * HD) + (size_t)(kvh * G + h) * HD + d] = o_final;
+                    const int bt = lane & 3;
+                    float4 l, hq;
+                    l.x = __shfl_sync(0xffffffffu, o_final, 4 * bt + 0);
+                    l.y = __shfl_sync(0xffffffffu, o_final, 4 * bt + 1);
+                    l.z = __shfl_sync(0xffffffffu, o_final, 4 * bt + 2);
+                    l.w = __shfl_sync(0xffffffffu, o_final, 4 * bt + 3);
+                    hq.x = __shfl_sync(0xffffffffu, o_final, 16 + 4 * bt + 0);
+                    hq.y = __shfl_sync(0xffffffffu, o_final, 16 + 4 * bt + 1);
+                    hq.z = __shfl_sync(0xffffffffu, o_final, 16 + 4 * bt + 2);
+                    hq.w = __shfl_sync(0xffffffffu, o_final, 16 + 4 * bt + 3);
+                    const int blk = ((kvh * G) * HD + (tid - lane)) >> 5;  // block of wo's K = H*HD input
+                    frag_build<MT>(l, hq, oact && lane < 4, bt, b, p.att_fbf + (size_t)blk * (16 * MT), p.att_foff + (size_t)blk * MT);
                 }
-                const float o = num / den;
-                p.attn_out[e] = o;
-                // a warp holds 32 consecutive head dims of one (stream, head) = one block of wo's input
-                const int bt = lane & 3;
-                float4 l, hq;
-                l.x = __shfl_sync(0xffffffffu, o, 4 * bt + 0);
-                l.y = __shfl_sync(0xffffffffu, o, 4 * bt + 1);
-                l.z = __shfl_sync(0xffffffffu, o, 4 * bt + 2);
-                l.w = __shfl_sync(0xffffffffu, o, 4 * bt + 3);
-                hq.x = __shfl_sync(0xffffffffu, o, 16 + 4 * bt + 0);
-                hq.y = __shfl_sync(0xffffffffu, o, 16 + 4 * bt + 1);
-                hq.z = __shfl_sync(0xffffffffu, o, 16 + 4 * bt + 2);
-                hq.w = __shfl_sync(0xffffffffu, o, 16 + 4 * bt + 3);
-                const int blk = ((e - lane) % (H * HD)) >> 5;
-                frag_build<MT>(l, hq, lane < 4, bt, b, p.att_fbf + (size_t)blk * (16 * MT), p.att_foff + (size_t)blk * MT);
             }
             asm volatile("fence.proxy.async;\n" ::: "memory");
         } else if (kind == MG_EMBED) {
@@ -889,6 +944,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 if (tid == 0) {
                     *p.d_pos = pos + 1;
                     *p.d_outpos = outpos + 1;
+                    *p.d_epoch = epoch + 1;
                 }
             }
         }

@@ -13,7 +13,7 @@ enum MegaKind : int {
     MG_MATVEC = 1,  // y = epi(norm?(x) . W^T), weights streamed through the CTA's TMA ring
     MG_ATTN = 2,    // RoPE + KV append + GQA attention of one layer
     MG_ARGMAX = 3,  // combine the per-CTA lm_head candidates, write the token, advance the counters
-    MG_ATTN_MERGE = 4,  // combine the key chunks' softmax states of MG_ATTN into the attention output
+    MG_ATTN_MERGE = 4,  // (unused: the last key chunk's CTA combines the chunks inside MG_ATTN)
 };
 
 // One grid-wide phase.  A grid barrier separates consecutive phases.
@@ -44,6 +44,7 @@ struct MegaOp {
     int track_argmax = 0;
     // MG_ATTN
     float *kc = nullptr, *vc = nullptr;  // this layer's caches [B][Hkv][max_seq][hd]
+    int layer = 0;
 };
 
 struct MegaParams {
@@ -60,6 +61,8 @@ struct MegaParams {
     int attn_chunks = 1;          // key chunks per (stream, kv head): spreads the KV walk over the grid
     float *att_acc = nullptr;     // [B*Hkv*chunks][G][hd] unnormalised weighted V per chunk
     float *att_ml = nullptr;      // [B*Hkv*chunks][G][2]  running max, sum of exp
+    int *att_flags = nullptr;     // [B*Hkv*chunks] chunk state published (value = epoch * 64 + layer + 1)
+    int *d_epoch = nullptr;       // decode steps executed by this session (never reset)
     // embedding (row-major planes of the tied table)
     const uint4 *emb_qs = nullptr;
     const __half *emb_d = nullptr;
@@ -85,7 +88,7 @@ struct MegaParams {
     // optional phase trace of CTA 0: 6 SM-clock stamps per op (start, staged, body done, barrier passed,
     // first weights ready | KV walked, last weight stage consumed)
     unsigned long long *trace = nullptr;
-    // experiment switches (VOX_MEGA_FLAGS): 1 no evict-first hint, 4 no gamma prefetch
+    // experiment switches (VOX_MEGA_FLAGS): 1 no evict-first hint, 2 no KV-cache L2 prefetch, 4 no norm-weight prefetch
     int flags = 0;
 };
 

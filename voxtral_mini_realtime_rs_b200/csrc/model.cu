@@ -492,6 +492,10 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
             s->mega_att_units = std::max(s->mega_grid, 8 * c.dec_kv_heads) + 8 * c.dec_kv_heads;
             s->mega_att_acc = s->arena.alloc_n<float>((size_t)s->mega_att_units * (c.dec_heads / c.dec_kv_heads) * c.dec_head_dim);
             s->mega_att_ml = s->arena.alloc_n<float>((size_t)s->mega_att_units * (c.dec_heads / c.dec_kv_heads) * 2);
+            s->mega_att_flags = s->arena.alloc_n<int>(s->mega_att_units);
+            s->mega_epoch = s->arena.alloc_n<int>(1);
+            CUDA_OK(cudaMemset(s->mega_att_flags, 0, sizeof(int) * s->mega_att_units));
+            CUDA_OK(cudaMemset(s->mega_epoch, 0, sizeof(int)));
             {
                 auto blocks = [](int K) { return (size_t)((K / 32 + 1) / 2) * 2; };
                 s->mega_xf_blocks = blocks(c.dec_dim);
@@ -767,10 +771,8 @@ bool Session::mega_prepare(int B) {
         a.kind = MG_ATTN;
         a.kc = kc + (size_t)j * layer_stride;
         a.vc = vc + (size_t)j * layer_stride;
+        a.layer = j;
         ops.push_back(a);
-        MegaOp am;
-        am.kind = MG_ATTN_MERGE;
-        ops.push_back(am);
         // wo: h += attn . Wo^T; leaves fragments of h x (ffn_norm x ADA) for w13
         matvec(l.wo, AF, x_dec, D, x_dec, EPI_RESIDUAL, nullptr, true, false, 2, XF, ffn_gamma_ada + (size_t)j * D);
         // w13: SwiGLU of the normed stream; leaves fragments of the activation for w2 (no plain copy)
@@ -786,7 +788,7 @@ bool Session::mega_prepare(int B) {
         ops.push_back(f);
     }
     (void)MT;
-    if (c.dec_ffn % 32 != 0 || (H * hd) % 32 != 0) ok = false;
+    if (c.dec_ffn % 32 != 0 || (H * hd) % 32 != 0 || c.dec_layers > 63) ok = false;
     // the residual epilogues and the embedding must leave exactly `parts` partial sums of squares
     if ((D + 15) / 16 != parts || D % 32 != 0) ok = false;
     if (!ok || (int)ops.size() > mega_ops_cap) return false;
@@ -826,8 +828,14 @@ void Session::decode_step(int B) {
         p.sin_t = m->dec_sin;
         p.attn_out = attn_dec;
         p.attn_chunks = std::max(1, std::min(16, std::min(mega_grid, mega_att_units - 8 * c.dec_kv_heads) / (B * c.dec_kv_heads)));
+        {
+            static const int env_nc = getenv("VOX_MEGA_NC") ? atoi(getenv("VOX_MEGA_NC")) : 0;
+            if (env_nc > 0 && env_nc <= p.attn_chunks) p.attn_chunks = env_nc;
+        }
         p.att_acc = mega_att_acc;
         p.att_ml = mega_att_ml;
+        p.att_flags = mega_att_flags;
+        p.d_epoch = mega_epoch;
         p.emb_qs = m->tok_emb.qs;
         p.emb_d = m->tok_emb.d;
         p.D = c.dec_dim;

@@ -134,6 +134,7 @@ struct Session {
     int *mega_am_idx = nullptr;
     float *mega_att_acc = nullptr, *mega_att_ml = nullptr;  // key-chunk softmax states (MG_ATTN -> MG_ATTN_MERGE)
     int mega_att_units = 0;
+    int *mega_att_flags = nullptr, *mega_epoch = nullptr;
     // activation fragments (decode_mega.cu frag_build): residual stream x norm weight, attention output, SwiGLU output
     uint2 *mega_xf_bf = nullptr, *mega_af_bf = nullptr, *mega_cf_bf = nullptr;
     float2 *mega_xf_off = nullptr, *mega_af_off = nullptr, *mega_cf_off = nullptr;
