@@ -449,6 +449,8 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
             CUDA_OK(cudaMemset(s->gemm_work.counters, 0, sizeof(int) * s->gemm_work.n_counters));
             const char *gv = getenv("VOX_GEMM");
             s->use_gemm_tc = !(gv && std::string(gv) == "simt");
+            const char *tv = getenv("VOX_MATVEC");
+            s->use_tc = !(tv && std::string(tv) == "simt");
             const char *av = getenv("VOX_ENC_ATTN");
             s->use_enc_attn_tc = !(av && std::string(av) == "simt");
         }
