@@ -330,7 +330,7 @@ def run_ours(args, rank, local_rank, world):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                "launch": f"one decode-step CUDA-graph replay for B={B} streams (Q4 matvec kernels + small ops)",
+                "launch": f"one decode step for B={B} streams = one launch of the persistent decode kernel (CUDA-graph replay)",
                 "algorithmic_bytes_per_launch": step_bytes, "ms_per_launch": step_ms_loop,
                 "single_stream": {"achieved": step_bytes / (s_step_ms / 1e3) / 1e9,
                                   "frac": step_bytes / (s_step_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
@@ -362,6 +362,11 @@ def run_ours(args, rank, local_rank, world):
                 "ids_match_device_path": same},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "single_stream": single,
+        # encoder + adapter of the same streams, algorithmic 1.235 TFLOP per 16 s stream
+        # (f32-equivalent; the tcgen05 GEMM spends 5 bf16 MMAs per product for f32-grade accuracy)
+        "encoder": {"ms": enc_ms / K, "algorithmic_tflop": 1.235 * B,
+                    "tflops": 1.235 * B / (enc_ms / K / 1e3) if enc_ms > 0 else None,
+                    "frac_of_bf16_dense_peak": (1.235 * B / (enc_ms / K / 1e3)) / peaks.get("bf16_tflops", 1700.9) if enc_ms > 0 else None},
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
