@@ -11,9 +11,8 @@ namespace vox {
 enum MegaKind : int {
     MG_EMBED = 0,   // x_dec[b] = audio[b][pos-?] + dequant(E[tok[b]])  (+ sums of squares for the first norm)
     MG_MATVEC = 1,  // y = epi(norm?(x) . W^T), weights streamed through the CTA's TMA ring
-    MG_ATTN = 2,    // RoPE + KV append + GQA attention of one layer
+    MG_ATTN = 2,    // RoPE + KV append + GQA attention of one layer (key chunks combined by the last chunk's CTA)
     MG_ARGMAX = 3,  // combine the per-CTA lm_head candidates, write the token, advance the counters
-    MG_ATTN_MERGE = 4,  // (unused: the last key chunk's CTA combines the chunks inside MG_ATTN)
 };
 
 // One grid-wide phase.  A grid barrier separates consecutive phases.

@@ -411,27 +411,6 @@ void launch_conv2_gemm(const float *in, const float *w, const float *bias, float
     gemm_launch<1, 1>(p, EPI_GELU, st);
 }
 
-// conv1 (128 -> C_out, k3 s2 p1) + GELU, direct: one CTA per (b, t_out), threads over C_out.
-// Input window (C_in x 3) staged in shared memory; weights [C_out][C_in][3] read as-is.
-__global__ void conv1_kernel(const float *__restrict__ mel, const float *__restrict__ w,
-                             const float *__restrict__ bias, float *__restrict__ out, int C_in, int T,
-                             int T_out, int C_out) {
-    extern __shared__ float win[];  // [C_in*3]
-    const int b = blockIdx.y, t = blockIdx.x;
-    for (int i = threadIdx.x; i < C_in * 3; i += blockDim.x) {
-        const int c = i / 3, tap = i - c * 3;
-        const int tin = 2 * t - 1 + tap;
-        win[i] = (tin >= 0 && tin < T) ? mel[((size_t)b * C_in + c) * T + tin] : 0.0f;
-    }
-    __syncthreads();
-    for (int o = threadIdx.x; o < C_out; o += blockDim.x) {
-        const float *wr = w + (size_t)o * C_in * 3;
-        float acc = 0.0f;
-        for (int i = 0; i < C_in * 3; ++i) acc = fmaf(wr[i], win[i], acc);
-        out[((size_t)b * T_out + t) * C_out + o] = gelu_erf(acc + bias[o]);
-    }
-}
-
 __global__ void transpose_mel_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int T) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
@@ -449,13 +428,6 @@ void launch_transpose_mel(const float *in, float *out, int B, int C, int T, cuda
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
     transpose_mel_kernel<<<grid, block, 0, st>>>(in, out, C, T);
     post_launch("transpose_mel");
-}
-
-void launch_conv1(const float *mel, const float *w, const float *bias, float *out, int B, int C_in, int T,
-                  int T_out, int C_out, cudaStream_t st) {
-    dim3 grid(T_out, B);
-    conv1_kernel<<<grid, 256, (size_t)C_in * 3 * sizeof(float), st>>>(mel, w, bias, out, C_in, T, T_out, C_out);
-    post_launch("conv1");
 }
 
 // =====================================================================================

@@ -77,16 +77,12 @@ struct GemmWork {
 };
 void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int ldy, const float *bias, const float *res,
                         int epi, const GemmWork *gw, cudaStream_t st);
-// conv2 as implicit GEMM: in [B][T_in][C_in] time-major, W [C_out][3*C_in] (k = tap*C_in + c),
+// conv1 / conv2 as implicit GEMM: in [B][T_in][C_in] time-major, W [C_out][3*C_in] (k = tap*C_in + c),
 // stride 2, pad 1, + bias, GELU -> out [B][T_out][C_out].
 void launch_conv2_gemm(const float *in, const float *w, const float *bias, float *out, int B, int T_in,
                        int T_out, int C_in, int C_out, cudaStream_t st);
 // [B][C][T] -> [B][T][C]
 void launch_transpose_mel(const float *in, float *out, int B, int C, int T, cudaStream_t st);
-// conv1: mel [B][C_in][T] channel-major, W [C_out][C_in][3] -> GELU -> out [B][T_out][C_out].
-void launch_conv1(const float *mel, const float *w, const float *bias, float *out, int B, int C_in, int T,
-                  int T_out, int C_out, cudaStream_t st);
-
 // y = x / sqrt(mean(x^2)+eps) * gamma (* scale, optional ADA vector)
 void launch_rmsnorm(const float *x, const float *gamma, const float *scale, float *y, int rows, int dim,
                     float eps, cudaStream_t st);

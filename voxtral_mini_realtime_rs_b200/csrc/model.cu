@@ -718,7 +718,6 @@ bool Session::mega_prepare(int B) {
     const int parts = (D + 15) / 16;
     std::vector<MegaOp> ops;
     bool ok = true;
-    const int MT = mega_plan.MT;
     struct Frag { uint2 *bf; float2 *off; };
     const Frag XF{mega_xf_bf, mega_xf_off}, AF{mega_af_bf, mega_af_off}, CF{mega_cf_bf, mega_cf_off};
     auto matvec = [&](const Q4Weight &w, Frag fin, float *y, int ldy, const float *res, int epi, const float *norm_w,
@@ -789,7 +788,6 @@ bool Session::mega_prepare(int B) {
         f.kind = MG_ARGMAX;
         ops.push_back(f);
     }
-    (void)MT;
     if (c.dec_ffn % 32 != 0 || (H * hd) % 32 != 0 || c.dec_layers > 63) ok = false;
     // the residual epilogues and the embedding must leave exactly `parts` partial sums of squares
     if ((D + 15) / 16 != parts || D % 32 != 0) ok = false;
