@@ -984,8 +984,19 @@ void launch_t(const MegaParams &p, const MegaPlan &plan, int grid, cudaStream_t 
                       "cudaFuncSetAttribute(decode_mega)");
         attr_set = true;
     }
-    decode_mega_kernel<MT, G, DPL><<<grid, MG_THREADS, plan.smem_bytes, st>>>(p);
-    cuda_check_mg(cudaGetLastError(), "decode_mega launch");
+    // cooperative launch: the runtime refuses the launch (instead of the grid barrier hanging) if the
+    // `grid` CTAs cannot all be resident at once
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(MG_THREADS);
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cuda_check_mg(cudaLaunchKernelEx(&cfg, decode_mega_kernel<MT, G, DPL>, p), "decode_mega launch");
     tc_count_launch("decode_mega");
 }
 
