@@ -184,8 +184,11 @@ int32_t vox_generate_step_with_cache(vox_session *s, const int32_t *ids, int32_t
                                      float *logits, size_t cap_floats);
 int32_t vox_session_cache_len(const vox_session *s, int32_t *len);             /* LayerCaches::seq_len */
 int32_t vox_session_reset(vox_session *s);                                       /* LayerCaches::reset  */
-/* debugging / parity: copy an internal activation by name ("enc_out","audio_embeds","conv",
- * "enc<i>","logits") to host */
+/* debugging / parity: copy an internal activation by name ("enc_out","audio_embeds","conv","enc<i>",
+ * "logits","ada") to host; "mega_trace" = SM-clock phase stamps of the last persistent decode step
+ * (6 floats per phase, microseconds); names of the form "<switch>_on|_off|_auto" (graph, tc, pdl, gemm_tc |
+ * gemm_simt, enc_attn_tc | enc_attn_simt, mega, capture) flip a kernel-selection switch and return no
+ * data */
 int32_t vox_session_debug_read(vox_session *s, const char *what, float *out, size_t cap_floats,
                                size_t *n_floats);
 /* per-kernel-family launch counter since creation (for bench.py's gpu_launches) */
