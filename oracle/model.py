@@ -179,6 +179,53 @@ class OracleModel:
         x = F.gelu(x)
         return self.linear(x, f"{ADAPTER}.2.weight")
 
+    # ---- encoder with KV cache (incremental API; SURVEY 8(f)-1: not yet behind the C ABI) -------------
+    def new_encoder_cache(self):
+        """Q4AudioEncoder::create_cache (model.rs:460-462): one dynamic KVCache per encoder layer."""
+        return [{"k": None, "v": None} for _ in range(self.cfg.enc_layers)]
+
+    def encoder_layer_with_cache(self, x: torch.Tensor, i: int, cache: dict) -> torch.Tensor:
+        """Q4EncoderLayer::forward_with_cache (model.rs:300-315) over Q4Attention::forward_with_cache
+        (model.rs:125-174): RoPE offset = cached length, K/V appended (kv_cache.rs:70-142), causal and
+        sliding-window masks with offset (masking.rs:50-107)."""
+        c = self.cfg
+        p = f"{ENC}.transformer.layers.{i}"
+        s = x.shape[0]
+        offset = 0 if cache["k"] is None else cache["k"].shape[0]
+        h = rms_norm(x, self.f32(f"{p}.attention_norm.weight"), c.norm_eps)
+        q = self.linear(h, f"{p}.attention.wq.weight", f"{p}.attention.wq.bias").reshape(s, c.enc_heads, c.enc_head_dim)
+        k = self.linear(h, f"{p}.attention.wk.weight").reshape(s, c.enc_heads, c.enc_head_dim)
+        v = self.linear(h, f"{p}.attention.wv.weight", f"{p}.attention.wv.bias").reshape(s, c.enc_heads, c.enc_head_dim)
+        q = apply_rope(q, self.enc_cos, self.enc_sin, offset)
+        k = apply_rope(k, self.enc_cos, self.enc_sin, offset)
+        cache["k"] = k if cache["k"] is None else torch.cat([cache["k"], k], 0)
+        cache["v"] = v if cache["v"] is None else torch.cat([cache["v"], v], 0)
+        a = self._attention(q, cache["k"], cache["v"], float(np.float32(c.enc_head_dim) ** np.float32(-0.5)),
+                            offset, c.enc_window)
+        x = self.linear(a, f"{p}.attention.wo.weight", f"{p}.attention.wo.bias") + x
+        h = rms_norm(x, self.f32(f"{p}.ffn_norm.weight"), c.norm_eps)
+        gate = F.silu(self.linear(h, f"{p}.feed_forward.w1.weight"))
+        up = self.linear(h, f"{p}.feed_forward.w3.weight")
+        return self.linear(gate * up, f"{p}.feed_forward.w2.weight", f"{p}.feed_forward.w2.bias") + x
+
+    def encoder_forward_with_cache(self, mel: np.ndarray, enc_cache: list) -> torch.Tensor:
+        """Q4AudioEncoder::forward_with_cache (model.rs:437-452): the conv stem runs on the chunk alone
+        (zero padding at the chunk edges, no carried state -- as upstream), the layers extend the caches."""
+        x = self.conv_downsample(torch.from_numpy(np.ascontiguousarray(mel, np.float32)))
+        x = x[0].transpose(0, 1).contiguous()
+        for i in range(self.cfg.enc_layers):
+            x = self.encoder_layer_with_cache(x, i, enc_cache[i])
+        return rms_norm(x, self.f32(f"{ENC}.transformer.norm.weight"), self.cfg.norm_eps)
+
+    def encode_audio_with_cache(self, mel: np.ndarray, enc_cache: list) -> torch.Tensor:
+        """Q4VoxtralModel::encode_audio_with_cache (model.rs:790-799)."""
+        x = self.encoder_forward_with_cache(mel, enc_cache)
+        rf = self.cfg.reshape_factor
+        s4 = x.shape[0] // rf
+        x = x[: s4 * rf].reshape(s4, self.cfg.enc_dim * rf)
+        x = F.gelu(self.linear(x, f"{ADAPTER}.0.weight"))
+        return self.linear(x, f"{ADAPTER}.2.weight")
+
     # ---- decoder ----------------------------------------------------------
     def ada_scales(self, t_embed: np.ndarray):
         """Q4AdaRmsNorm (model.rs:250-255): 1 + w2(gelu(w0(t))) per layer (t constant)."""

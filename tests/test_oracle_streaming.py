@@ -1,0 +1,49 @@
+"""Oracle-internal consistency of the incremental encoder API (reference model.rs:437-452, 790-799;
+Q4Attention::forward_with_cache 125-174; masks with offset masking.rs:50-107).  This is the checker for
+the streaming-session row of SURVEY 8(f); the C ABI does not expose it yet, so there is no GPU side."""
+import numpy as np
+import torch
+
+from oracle import mel as omel
+
+
+def _mel(seconds, seed):
+    return omel.mel_tensor_from_audio(omel.peak_normalize(omel.speechlike(seconds, seed)))
+
+
+def test_cached_encoder_single_chunk_equals_batch(tiny_oracle):
+    mel = _mel(3.0, 5)
+    full = tiny_oracle.encode_audio(mel)
+    cached = tiny_oracle.encode_audio_with_cache(mel, tiny_oracle.new_encoder_cache())
+    assert full.shape == cached.shape
+    assert torch.equal(full, cached)  # same operations in the same order
+
+
+def test_cached_encoder_chunks_extend_the_cache(tiny_oracle):
+    """Two chunks through the cache == the uncached layers over the concatenated per-chunk conv
+    outputs: the offset RoPE / causal / sliding-window bookkeeping is position-exact.  The tiny model's
+    window (20) is smaller than the sequence, so the offset window mask bites."""
+    o = tiny_oracle
+    mel = _mel(4.0, 6)
+    t_split = 160  # mel frames; a multiple of 4 so both chunks give whole encoder frames
+    c1, c2 = mel[:, :, :t_split], mel[:, :, t_split:]
+    cache = o.new_encoder_cache()
+    y1 = o.encoder_forward_with_cache(c1, cache)
+    y2 = o.encoder_forward_with_cache(c2, cache)
+    assert cache[0]["k"].shape[0] == y1.shape[0] + y2.shape[0] > o.cfg.enc_window
+    # reference computation: per-chunk conv stems (as upstream: no carried conv state), then the
+    # whole-sequence layers at offset 0
+    x = torch.cat([o.conv_downsample(torch.from_numpy(np.ascontiguousarray(c, np.float32)))[0].transpose(0, 1)
+                   for c in (c1, c2)], 0).contiguous()
+    for i in range(o.cfg.enc_layers):
+        x = o.encoder_layer(x, i)
+    from oracle.model import ENC, rms_norm
+    ref = rms_norm(x, o.f32(f"{ENC}.transformer.norm.weight"), o.cfg.norm_eps)
+    got = torch.cat([y1, y2], 0)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    # and chunking is NOT the same as the whole-utterance stem (zero padding at the cut): the streaming
+    # session of SURVEY 8(f)-1 has to carry conv state to reproduce transcribe_streaming exactly
+    whole = o.encoder_forward(mel)
+    assert whole.shape == ref.shape
+    assert (whole - ref).abs().max().item() > 1e-4
