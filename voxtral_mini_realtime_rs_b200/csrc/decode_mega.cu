@@ -61,6 +61,9 @@ constexpr long long MG_SPIN_CYCLES = 4000000000ll;  // ~2 s: watchdog
 __host__ __device__ constexpr int mg_nt(int MT) { return MT <= 2 ? 4 : 2; }
 // epilogue outputs waiting to become fragments: up to two 32-value blocks x MT tokens per tile group
 __host__ __device__ constexpr int mg_vals(int MT) { return (MT <= 2 ? 2 : 1) * 32 * MT; }
+static_assert(mg_vals(1) >= 2 * mg_nt(1) * 1 && mg_vals(2) >= 2 * mg_nt(2) * 2 && mg_vals(4) >= 2 * mg_nt(4) * 4 &&
+                  mg_vals(8) >= 2 * mg_nt(8) * 8,
+              "vals also holds the lm_head phase's per-slot argmax candidates");
 // barriers + rinv + red[2][16 warps][NT*16*MT] + acc_tile[MG_ACC_TILES][16*MT] + vals
 __host__ __device__ constexpr int mg_misc_bytes(int MT) {
     return ((432 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT + 4 * mg_vals(MT)) + 127) & ~127;
@@ -609,8 +612,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                     const int ox = __shfl_xor_sync(0xffffffffu, best_i, o);
                     amax_combine(best_v, best_i, ov, ox);
                 }
-                float *cv = red;  // red is idle between ops: [NT][MT] values, then [NT][MT] indices
-                int *ci = reinterpret_cast<int *>(red + NT * MT);
+                // `vals` is idle in this op (only fragment-producing ops use it) -- not `red`, which slower epilogue
+                // warps may still be reading: [NT][MT] values, then [NT][MT] indices
+                float *cv = vals;
+                int *ci = reinterpret_cast<int *>(vals + NT * MT);
                 if ((tid & 15) == 0 && tid < NT * 16 * MT) {
                     cv[tid >> 4] = best_v;
                     ci[tid >> 4] = best_i;
@@ -623,8 +628,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 if (tid < B) {
                     float bv = -INFINITY;
                     int bx = 0x7fffffff;
-                    const float *cv = red;
-                    const int *ci = reinterpret_cast<const int *>(red + NT * MT);
+                    const float *cv = vals;
+                    const int *ci = reinterpret_cast<const int *>(vals + NT * MT);
 #pragma unroll
                     for (int u = 0; u < NT; ++u) amax_combine(bv, bx, cv[u * MT + tid], ci[u * MT + tid]);
                     p.am_vals[(size_t)cta * 8 + tid] = bv;
