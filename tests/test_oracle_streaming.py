@@ -47,3 +47,29 @@ def test_cached_encoder_chunks_extend_the_cache(tiny_oracle):
     whole = o.encoder_forward(mel)
     assert whole.shape == ref.shape
     assert (whole - ref).abs().max().item() > 1e-4
+
+
+def test_streaming_session_equals_offline_transcribe(tiny_oracle):
+    """Feeding the padded utterance 80 ms at a time (and in ragged pieces) through the incremental pipeline of
+    oracle/streaming.py yields the ids of the whole-utterance transcribe_streaming (model.rs:873-963), every
+    token as soon as its inputs are final: the carried state / lookahead table in that module is sufficient."""
+    from oracle.streaming import StreamingOracle
+    o = tiny_oracle
+    audio = omel.peak_normalize(omel.speechlike(4.0, 21))
+    t_embed = omel.time_embedding(6.0, o.cfg.dec_dim)
+    info = {}
+    offline = o.transcribe_streaming(omel.mel_tensor_from_audio(audio), t_embed, info=info)
+    for piece in (1280, 3001):
+        st = StreamingOracle(o, t_embed)
+        got, emitted_before_end = [], 0
+        for a in range(0, audio.size, piece):
+            got += st.feed(audio[a:a + piece])
+        emitted_before_end = len(got)
+        got += st.finish()
+        assert got == offline, (piece, got, offline, min(info["margins"]))
+        emb = torch.stack(st.audio_embeds)
+        assert emb.shape == info["audio_embeds"].shape
+        assert (emb - info["audio_embeds"]).abs().max().item() < 2e-5 * max(1.0, info["audio_embeds"].abs().max().item())
+        # tokens really stream: most are out before the end of the audio (the rest wait for the right padding)
+        assert 0 < emitted_before_end < len(offline)
+        assert len(offline) - emitted_before_end <= 12
