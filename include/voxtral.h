@@ -78,6 +78,13 @@ typedef struct {
 int32_t vox_chunk_plan(size_t n_samples, size_t max_mel_frames, size_t overlap_frames,
                        vox_chunk *out, size_t cap, size_t *n_chunks);            /* chunk_audio chunk.rs:122-166 */
 int32_t vox_time_embedding(float t, int32_t dim, float *out);                    /* TimeEmbedding::embed time_embedding.rs:41-71 */
+/* Streaming-session bookkeeping (the incremental forms of mel.rs:175-182, conv.rs:47-48,
+ * adapter.rs:115-121, model.rs:883-960): how far each stage can advance once `n_samples` samples of the PADDED
+ * signal are known (`ended` != 0: the right padding is in, the stream is complete).  An output is counted only
+ * when every input it reads is final, so the counts never have to be revised:
+ * out[0] log-mel frames, out[1] conv1 frames, out[2] encoder frames, out[3] audio embeddings (decoder positions
+ * with audio), out[4] token ids that can be emitted.  Checked against oracle/streaming.py. */
+int32_t vox_stream_progress(size_t n_samples, int32_t ended, int32_t reshape_factor, int32_t prefix_len, int64_t out[5]);
 
 /* ------------------------------------------------------------------ mel front-end (GPU)
  * MelSpectrogram::{new, num_frames, compute_log}, src/audio/mel.rs:73,175,128 */

@@ -73,3 +73,29 @@ def test_streaming_session_equals_offline_transcribe(tiny_oracle):
         # tokens really stream: most are out before the end of the audio (the rest wait for the right padding)
         assert 0 < emitted_before_end < len(offline)
         assert len(offline) - emitted_before_end <= 12
+
+
+def test_stream_progress_matches_streaming_oracle(vx, tiny_oracle):
+    """vox_stream_progress (host bookkeeping of a streaming session) against the counters of the incremental
+    oracle at every 80 ms step and at the end of the stream."""
+    from oracle.streaming import StreamingOracle
+    o = tiny_oracle
+    audio = omel.peak_normalize(omel.speechlike(2.5, 9))
+    st = StreamingOracle(o, omel.time_embedding(6.0, o.cfg.dec_dim))
+
+    def check(ended):
+        got = vx.stream_progress(st.samples.size, ended, o.cfg.reshape_factor, 38)
+        assert got == (len(st.mel), len(st.c1), st.c2_count, len(st.audio_embeds), len(st.ids)), (st.samples.size, ended, got)
+
+    check(False)
+    for a in range(0, audio.size, 1280):
+        st.feed(audio[a:a + 1280])
+        check(False)
+    st.finish()
+    check(True)
+    # whole-utterance counts of the 16 s configuration (SURVEY 8: 375 040 samples -> 2344 / 1172 / 586 / 146 / 108)
+    assert vx.stream_progress(375040, True) == (2344, 1172, 586, 146, 108)
+    # audio embedding p needs samples up to 2560 p + 2600
+    for p in (0, 1, 37, 100):
+        need = 2560 * p + 2600
+        assert vx.stream_progress(need, False)[3] == p + 1 and vx.stream_progress(need - 1, False)[3] == p

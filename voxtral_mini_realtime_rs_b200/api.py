@@ -83,6 +83,7 @@ _SIGS = {
     "vox_pad_config_default": (None, [C.POINTER(_PadConfig)]),
     "vox_pad_audio_len": (C.c_size_t, [C.c_size_t, C.POINTER(_PadConfig)]),
     "vox_pad_audio": (C.c_int32, [_P, C.c_size_t, C.POINTER(_PadConfig), _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "vox_stream_progress": (C.c_int32, [C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "vox_chunk_plan": (C.c_int32, [C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(_Chunk), C.c_size_t,
                                    C.POINTER(C.c_size_t)]),
     "vox_time_embedding": (C.c_int32, [C.c_float, C.c_int32, _P]),
@@ -293,6 +294,14 @@ def chunk_audio(n_samples: int, max_mel_frames: int = 1500, overlap_frames: int 
     arr = (_Chunk * max(cnt.value, 1))()
     _check(lib().vox_chunk_plan(n_samples, max_mel_frames, overlap_frames, arr, cnt.value, C.byref(cnt)))
     return [(arr[i].start_sample, arr[i].end_sample, arr[i].index, bool(arr[i].is_last)) for i in range(cnt.value)]
+
+
+def stream_progress(n_samples: int, ended: bool = False, reshape_factor: int = 4, prefix_len: int = 38):
+    """Final outputs per stage once `n_samples` padded samples are known: (mel frames, conv1 frames, encoder
+    frames, audio embeddings, emit-able token ids) -- the bookkeeping of a streaming session."""
+    out = (C.c_int64 * 5)()
+    _check(lib().vox_stream_progress(n_samples, 1 if ended else 0, reshape_factor, prefix_len, out))
+    return tuple(int(v) for v in out)
 
 
 def needs_chunking(n_samples: int, max_mel_frames: int = 1500) -> bool:

@@ -113,4 +113,32 @@ void mel_filterbank(float *fb /* [128][201] */) {
     }
 }
 
+// Stage i's output t is final when the inputs it reads are: an STFT frame needs samples [160 t - 200, 160 t + 200)
+// (centre padding; the reflect pad only ever sees the zeros pad_audio adds), a k3 s2 p1 convolution output needs input
+// frame 2 t + 1, an audio embedding needs `reshape_factor` encoder frames, decoder position p needs embedding p - 1
+// (the prefill needs the first `prefix_len`), and the last embedding of a finished stream is never consumed
+// (model.rs:938: the loop stops at S - 1).
+void stream_progress(size_t n_samples, bool ended, int reshape_factor, int prefix_len, int64_t out[5]) {
+    const int64_t n = (int64_t)n_samples;
+    auto conv_final = [&](int64_t t_in) -> int64_t {
+        if (t_in <= 0) return 0;
+        if (ended) return (t_in + 2 - 3) / 2 + 1;   // conv.rs:47-48
+        return t_in >= 2 ? (t_in - 2) / 2 + 1 : 0;   // largest t with 2 t + 1 <= t_in - 1
+    };
+    const int64_t mel = ended ? n / 160 : (n >= 200 ? (n - 200) / 160 + 1 : 0);
+    const int64_t c1 = conv_final(mel);
+    const int64_t enc = conv_final(c1);
+    const int64_t emb = reshape_factor > 0 ? enc / reshape_factor : 0;
+    int64_t ids = 0;
+    if (emb >= prefix_len) {
+        const int64_t last_pos = ended ? emb - 1 : emb;
+        ids = 1 + (last_pos > prefix_len ? last_pos - prefix_len : 0);
+    }
+    out[0] = mel;
+    out[1] = c1;
+    out[2] = enc;
+    out[3] = emb;
+    out[4] = ids;
+}
+
 }  // namespace vox

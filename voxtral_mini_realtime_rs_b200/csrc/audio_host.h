@@ -17,6 +17,8 @@ size_t pad_left(const vox_pad_config &c);
 size_t pad_right(const vox_pad_config &c, size_t total);
 size_t pad_audio_len(size_t n, const vox_pad_config &c);
 std::vector<vox_chunk> chunk_plan(size_t n, size_t max_mel_frames, size_t overlap_frames);
+// incremental stage counts for n known samples of the padded signal (see include/voxtral.h vox_stream_progress)
+void stream_progress(size_t n_samples, bool ended, int reshape_factor, int prefix_len, int64_t out[5]);
 void time_embedding(float t, int dim, float *out);
 void hann_window(int n, float *out);
 void mel_filterbank(float *fb);

@@ -187,6 +187,14 @@ int32_t vox_chunk_plan(size_t n, size_t max_mel_frames, size_t overlap, vox_chun
     }
     VOX_API_END
 }
+int32_t vox_stream_progress(size_t n_samples, int32_t ended, int32_t reshape_factor, int32_t prefix_len, int64_t out[5]) {
+    VOX_API_BEGIN
+    REQUIRE(out);
+    VOX_CHECK(reshape_factor > 0 && prefix_len > 0, VOX_EINVAL, "stream_progress: reshape_factor %d / prefix_len %d must be positive",
+              reshape_factor, prefix_len);
+    stream_progress(n_samples, ended != 0, reshape_factor, prefix_len, out);
+    VOX_API_END
+}
 int32_t vox_time_embedding(float t, int32_t dim, float *out) {
     VOX_API_BEGIN
     REQUIRE(out);
