@@ -108,15 +108,25 @@ _LIB = None
 
 
 def build_c(force: bool = False) -> str:
+    """gcc build of the C restatements: q4_ref.c / mel_ref.c strict (-O2, no FMA contraction: the
+    checker's arithmetic), q4_fast.c vectorised (-O3 -mavx2 -mfma: the timed CPU baseline)."""
     so = os.path.join(_HERE, "liboracle_ref.so")
-    srcs = [os.path.join(_HERE, "q4_ref.c"), os.path.join(_HERE, "mel_ref.c")]
+    strict = [os.path.join(_HERE, "q4_ref.c"), os.path.join(_HERE, "mel_ref.c")]
+    fast = [os.path.join(_HERE, "q4_fast.c")]
     if not force and os.path.exists(so) and all(
-        os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs
+        os.path.getmtime(so) >= os.path.getmtime(s) for s in strict + fast
     ):
         return so
-    cmd = ["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-march=native", "-ffp-contract=off",
-           "-o", so] + srcs + ["-lm"]
-    subprocess.check_call(cmd)
+    objs = []
+    for src in strict:
+        o = src[:-2] + ".o"
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fPIC", "-march=native", "-ffp-contract=off", "-c", src, "-o", o])
+        objs.append(o)
+    for src in fast:
+        o = src[:-2] + ".o"
+        subprocess.check_call(["gcc", "-O3", "-fopenmp", "-fPIC", "-mavx2", "-mfma", "-ffp-contract=fast", "-c", src, "-o", o])
+        objs.append(o)
+    subprocess.check_call(["gcc", "-shared", "-fopenmp", "-o", so] + objs + ["-lm"])
     return so
 
 
@@ -128,11 +138,18 @@ def _lib():
         _LIB.oracle_q4_matmul.argtypes = [f, f, f, f, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_int]
         _LIB.oracle_q4_matmul.restype = None
+        _LIB.oracle_q4_matmul_fast.argtypes = [f, f, f, f, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        _LIB.oracle_q4_matmul_fast.restype = None
         _LIB.oracle_q4_dequant.argtypes = [f, f, ctypes.c_longlong]
         _LIB.oracle_q4_dequant.restype = None
         _LIB.oracle_mel_compute_log.argtypes = [f, ctypes.c_longlong, f]
         _LIB.oracle_mel_compute_log.restype = ctypes.c_longlong
     return _LIB
+
+
+# bench.py sets this for its timed CPU legs: the vectorised re-association (q4_fast.c) instead of the strict
+# shader-order loop (q4_ref.c).  Tests never set it: the checker's arithmetic is the strict one.
+FAST = False
 
 
 def q4_matmul_c(x: np.ndarray, raw: np.ndarray, n: int, k: int, bias: np.ndarray | None = None,
@@ -148,8 +165,8 @@ def q4_matmul_c(x: np.ndarray, raw: np.ndarray, n: int, k: int, bias: np.ndarray
     b = None
     if bias is not None:
         b = np.ascontiguousarray(bias, np.float32)
-    _lib().oracle_q4_matmul(x.ctypes.data, raw.ctypes.data, y.ctypes.data,
-                            b.ctypes.data if b is not None else None, m, n, k, threads)
+    fn = _lib().oracle_q4_matmul_fast if FAST else _lib().oracle_q4_matmul
+    fn(x.ctypes.data, raw.ctypes.data, y.ctypes.data, b.ctypes.data if b is not None else None, m, n, k, threads)
     return y
 
 

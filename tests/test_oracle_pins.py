@@ -202,3 +202,24 @@ def test_tokenizer_reference_golden_if_available():        # mod.rs:255-268 (nee
         pytest.skip("real tekken.json not available offline (SURVEY F3)")
     t = otok.VoxtralTokenizer.from_file(p)
     assert t.decode([1362, 19135, 1294, 1278, 4618, 40307, 3910, 1046]) == " I spoke in the original phonograph."
+
+
+def test_vectorised_port_agrees_with_strict_order_port():
+    """oracle/q4_fast.c (the timed CPU baseline of bench.py) against oracle/q4_ref.c (the checker's strict
+    shader-order arithmetic): same result to f32 re-association noise, for matvec and small-M shapes, odd
+    block counts and a bias."""
+    rng = np.random.default_rng(11)
+    for (m, n, k) in [(1, 96, 3072), (3, 50, 160), (8, 33, 96)]:
+        raw = np.empty((n * k // 32, 18), np.uint8)
+        raw[:, :2] = rng.uniform(0.002, 0.02, n * k // 32).astype(np.float16).view(np.uint8).reshape(-1, 2)
+        raw[:, 2:] = rng.integers(0, 256, (n * k // 32, 16), dtype=np.uint8)
+        raw = raw.reshape(-1)
+        x = rng.standard_normal((m, k)).astype(np.float32)
+        bias = rng.standard_normal(n).astype(np.float32)
+        strict = oq4.q4_matmul_c(x, raw, n, k, bias, threads=2)
+        oq4.FAST = True
+        try:
+            fast = oq4.q4_matmul_c(x, raw, n, k, bias, threads=2)
+        finally:
+            oq4.FAST = False
+        assert np.abs(fast - strict).max() < 2e-5 * max(1.0, np.abs(strict).max())
