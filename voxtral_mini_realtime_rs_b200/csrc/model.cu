@@ -877,6 +877,13 @@ void Session::reset() {
     CUDA_OK(cudaMemsetAsync(d_pos, 0, sizeof(int), st));
     CUDA_OK(cudaMemsetAsync(d_outpos, 0, sizeof(int), st));
     cache_len = 0;
+    // the persistent kernel's attention-chunk flags carry epoch * 64 + layer + 1 (int): re-base the device
+    // epoch long before that can overflow (2^24 steps ~ 10 hours of continuous decoding)
+    if (mega_steps_host > (1u << 24)) {
+        CUDA_OK(cudaMemsetAsync(mega_att_flags, 0, sizeof(int) * mega_att_units, st));
+        CUDA_OK(cudaMemsetAsync(mega_epoch, 0, sizeof(int), st));
+        mega_steps_host = 0;
+    }
 }
 
 // Q4VoxtralModel::transcribe_streaming (model.rs:873-963).  Expects the mel in s->mel; records
@@ -905,6 +912,7 @@ int Session::transcribe_from_mel(int B, int T, int32_t *out_ids, size_t cap_ids,
         launch_advance(d_pos, P, d_outpos, 1, st);
         CUDA_OK(cudaEventRecord(ev[4], st));
         const int steps = S4 - P - 1;
+        if (steps > 0) mega_steps_host += (unsigned)steps;  // upper bound of the device epoch's advance
         if (steps > 0) {
             int done = 0;
             if (use_graph) {

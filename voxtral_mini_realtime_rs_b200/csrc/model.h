@@ -135,6 +135,7 @@ struct Session {
     float *mega_att_acc = nullptr, *mega_att_ml = nullptr;  // key-chunk softmax states (MG_ATTN -> MG_ATTN_MERGE)
     int mega_att_units = 0;
     int *mega_att_flags = nullptr, *mega_epoch = nullptr;
+    unsigned mega_steps_host = 0;  // decode steps since the device epoch was last re-based (Session::reset)
     // activation fragments (decode_mega.cu frag_build): residual stream x norm weight, attention output, SwiGLU output
     uint2 *mega_xf_bf = nullptr, *mega_af_bf = nullptr, *mega_cf_bf = nullptr;
     float2 *mega_xf_off = nullptr, *mega_af_off = nullptr, *mega_cf_off = nullptr;
