@@ -180,9 +180,12 @@ class OracleModel:
         return self.linear(x, f"{ADAPTER}.2.weight")
 
     # ---- encoder with KV cache (incremental API; SURVEY 8(f)-1: not yet behind the C ABI) -------------
-    def new_encoder_cache(self):
-        """Q4AudioEncoder::create_cache (model.rs:460-462): one dynamic KVCache per encoder layer."""
-        return [{"k": None, "v": None} for _ in range(self.cfg.enc_layers)]
+    def new_encoder_cache(self, evict: bool = False):
+        """Q4AudioEncoder::create_cache (model.rs:460-462): one dynamic KVCache per encoder layer.
+        `evict`: drop keys that no future query can see (older than the sliding window) while keeping ABSOLUTE
+        positions for RoPE and the masks -- the bounded-memory form a long-running streaming session needs.
+        (Upstream's KVCache::apply_sliding_window, kv_cache.rs:176-203, is unused and would re-base positions.)"""
+        return [{"k": None, "v": None, "base": 0, "evict": evict} for _ in range(self.cfg.enc_layers)]
 
     def encoder_layer_with_cache(self, x: torch.Tensor, i: int, cache: dict) -> torch.Tensor:
         """Q4EncoderLayer::forward_with_cache (model.rs:300-315) over Q4Attention::forward_with_cache
@@ -191,7 +194,14 @@ class OracleModel:
         c = self.cfg
         p = f"{ENC}.transformer.layers.{i}"
         s = x.shape[0]
-        offset = 0 if cache["k"] is None else cache["k"].shape[0]
+        base = cache.get("base", 0)                                   # absolute position of the first cached key
+        offset = base + (0 if cache["k"] is None else cache["k"].shape[0])
+        if cache.get("evict") and cache["k"] is not None and c.enc_window is not None:
+            drop = min(max(offset - c.enc_window - base, 0), cache["k"].shape[0])   # keys older than offset - window
+            if drop > 0:
+                cache["k"], cache["v"] = cache["k"][drop:], cache["v"][drop:]
+                base += drop
+                cache["base"] = base
         h = rms_norm(x, self.f32(f"{p}.attention_norm.weight"), c.norm_eps)
         q = self.linear(h, f"{p}.attention.wq.weight", f"{p}.attention.wq.bias").reshape(s, c.enc_heads, c.enc_head_dim)
         k = self.linear(h, f"{p}.attention.wk.weight").reshape(s, c.enc_heads, c.enc_head_dim)
@@ -201,7 +211,7 @@ class OracleModel:
         cache["k"] = k if cache["k"] is None else torch.cat([cache["k"], k], 0)
         cache["v"] = v if cache["v"] is None else torch.cat([cache["v"], v], 0)
         a = self._attention(q, cache["k"], cache["v"], float(np.float32(c.enc_head_dim) ** np.float32(-0.5)),
-                            offset, c.enc_window)
+                            offset - base, c.enc_window)   # masks only depend on position differences
         x = self.linear(a, f"{p}.attention.wo.weight", f"{p}.attention.wo.bias") + x
         h = rms_norm(x, self.f32(f"{p}.ffn_norm.weight"), c.norm_eps)
         gate = F.silu(self.linear(h, f"{p}.feed_forward.w1.weight"))

@@ -99,3 +99,23 @@ def test_stream_progress_matches_streaming_oracle(vx, tiny_oracle):
     for p in (0, 1, 37, 100):
         need = 2560 * p + 2600
         assert vx.stream_progress(need, False)[3] == p + 1 and vx.stream_progress(need - 1, False)[3] == p
+
+
+def test_encoder_cache_eviction_keeps_results(tiny_oracle):
+    """Dropping keys older than the sliding window (absolute positions kept for RoPE and masks) does not change
+    the encoder output: the bounded-memory KV ring a long streaming session needs.  Fed frame-by-frame-ish
+    (8 mel frames = 2 encoder frames per call) so that eviction happens many times."""
+    o = tiny_oracle
+    mel = _mel(6.0, 33)                                   # ~ 186 encoder frames >> window 20
+    t = (mel.shape[2] // 8) * 8
+    keep, evict = o.new_encoder_cache(), o.new_encoder_cache(evict=True)
+    outs_k, outs_e = [], []
+    for a in range(0, t, 8):
+        outs_k.append(o.encoder_forward_with_cache(mel[:, :, a:a + 8], keep))
+        outs_e.append(o.encoder_forward_with_cache(mel[:, :, a:a + 8], evict))
+    yk, ye = torch.cat(outs_k), torch.cat(outs_e)
+    assert yk.shape == ye.shape and yk.shape[0] > 4 * o.cfg.enc_window
+    assert (yk - ye).abs().max().item() < 2e-5 * max(1.0, yk.abs().max().item())
+    assert keep[0]["k"].shape[0] == yk.shape[0]
+    assert evict[0]["k"].shape[0] <= o.cfg.enc_window + 2   # bounded: window + the chunk being processed
+    assert evict[0]["base"] + evict[0]["k"].shape[0] == yk.shape[0]
