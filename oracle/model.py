@@ -135,6 +135,26 @@ class OracleModel:
         out = torch.matmul(attn, vh)                             # [H,Sq,hd]
         return out.permute(1, 0, 2).reshape(sq, h * hd)
 
+    def encoder_attention_block(self, h: torch.Tensor, i: int) -> torch.Tensor:
+        """Q4Attention::forward (model.rs:77-122) on already-normed input h [S, d]: q/k/v (+biases), RoPE,
+        masked softmax attention, wo (+bias).  No residual."""
+        c = self.cfg
+        p = f"{ENC}.transformer.layers.{i}"
+        s = h.shape[0]
+        q = self.linear(h, f"{p}.attention.wq.weight", f"{p}.attention.wq.bias").reshape(s, c.enc_heads, c.enc_head_dim)
+        k = self.linear(h, f"{p}.attention.wk.weight").reshape(s, c.enc_heads, c.enc_head_dim)
+        v = self.linear(h, f"{p}.attention.wv.weight", f"{p}.attention.wv.bias").reshape(s, c.enc_heads, c.enc_head_dim)
+        q = apply_rope(q, self.enc_cos, self.enc_sin, 0)
+        k = apply_rope(k, self.enc_cos, self.enc_sin, 0)
+        a = self._attention(q, k, v, float(np.float32(c.enc_head_dim) ** np.float32(-0.5)), 0, c.enc_window)
+        return self.linear(a, f"{p}.attention.wo.weight", f"{p}.attention.wo.bias")
+
+    def swiglu(self, h: torch.Tensor, prefix: str, bias: bool = False) -> torch.Tensor:
+        """Q4FeedForward::forward (model.rs:220-224): w2(silu(w1 h) * w3 h)."""
+        gate = F.silu(self.linear(h, f"{prefix}.feed_forward.w1.weight"))
+        up = self.linear(h, f"{prefix}.feed_forward.w3.weight")
+        return self.linear(gate * up, f"{prefix}.feed_forward.w2.weight", f"{prefix}.feed_forward.w2.bias" if bias else None)
+
     def encoder_layer(self, x: torch.Tensor, i: int) -> torch.Tensor:
         c = self.cfg
         p = f"{ENC}.transformer.layers.{i}"
@@ -290,6 +310,19 @@ class OracleModel:
     def lm_head(self, h: torch.Tensor) -> torch.Tensor:
         """model.rs:680-691 (tied embeddings)."""
         return self.linear(h, TOK_EMB)
+
+    def forward_streaming(self, mel: np.ndarray, token_ids, t_embed: np.ndarray, audio_embeds=None,
+                          return_hidden: bool = False):
+        """Q4VoxtralModel::forward_streaming (model.rs:801-814): logits [S, V] for a full teacher-forced pass,
+        inputs = audio_embeds + embed(token_ids), no cache carried in.  This is the graph the reference's
+        scripts/compare_full_forward.py:262-361 evaluates (token_ids = [32]*S)."""
+        audio = self.encode_audio(mel) if audio_embeds is None else audio_embeds
+        ids = list(token_ids)
+        assert len(ids) == audio.shape[0]
+        x = audio + self.embed_tokens(ids)
+        hidden = self.decoder_forward_with_cache(x, self.ada_scales(t_embed), self.new_cache())
+        logits = self.lm_head(hidden)
+        return (logits, hidden) if return_hidden else logits
 
     def transcribe_streaming(self, mel: np.ndarray, t_embed: np.ndarray, audio_embeds=None,
                              info: dict | None = None):

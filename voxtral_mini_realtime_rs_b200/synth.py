@@ -255,6 +255,42 @@ def write_synthetic_gguf(path: str, cfg: VoxtralConfig, seed: int = 42, f16_norm
     return {"bytes": total, "q4_bytes": q4b, "tensors": len(metas)}
 
 
+def refshape_config() -> VoxtralConfig:
+    """Every dimension the reference's torch scripts hard-code (scripts/generate_padded_reference.py:95-187,
+    compare_full_forward.py:278-361: 1280 / 32x64 / 32 layers, 3072 / 32:8x128 / 26 layers) with small FFNs and
+    vocabulary -- the model tests/golden/make_reference_fixtures.py runs the reference Python on."""
+    return VoxtralConfig(enc_ffn=512, dec_ffn=512, vocab=4096)
+
+
+def build_aliased_gguf_bytes(cfg: VoxtralConfig, seed: int, unique: int = 2) -> bytes:
+    """In-memory GGUF whose layers i >= `unique` alias the bytes of layer i % unique (several names, one offset
+    in the tensor index -- legal GGUF), so a full-depth model costs `unique` layers of bytes and of generation
+    time.  Deterministic; data 32-byte aligned."""
+    def canon(name):
+        for pre in (f"{ENC}.transformer.layers.", "layers."):
+            if name.startswith(pre):
+                idx, rest = name[len(pre):].split(".", 1)
+                return f"{pre}{int(idx) % unique}.{rest}"
+        return name
+
+    metas, blobs, offs, off = [], [], {}, 0
+    for name, dt, shape in tensor_manifest(cfg):
+        c = canon(name)
+        if c not in offs:
+            off = (off + ALIGN - 1) // ALIGN * ALIGN
+            data = synth_tensor_bytes(c, dt, shape, seed).tobytes()
+            offs[c] = off
+            blobs.append((off, data))
+            off += len(data)
+        metas.append((name, dt, shape, offs[c]))
+    hdr = header_bytes(metas, [("general.architecture", "voxtral")] + cfg.kv_items())
+    out = bytearray(hdr)
+    for o, data in blobs:
+        out.extend(b"\0" * (len(hdr) + o - len(out)))
+        out.extend(data)
+    return bytes(out)
+
+
 # ------------------------------------------------------------------------------ signals
 def sine_16k(seconds: float, freq: float = 440.0, amp: float = 0.5) -> np.ndarray:
     """benches/audio.rs:13-18."""
