@@ -189,6 +189,21 @@ int32_t vox_transcribe_pcm_dev(vox_session *s, const float *samples_dev, int32_t
  * host; appends to the session's decoder KV cache (vox_session_reset clears it). */
 int32_t vox_generate_step_with_cache(vox_session *s, const int32_t *ids, int32_t b, int32_t m,
                                      float *logits, size_t cap_floats);
+/* forward_streaming (model.rs:801-814): teacher-forced full pass from mel: decoder inputs = audio_embeds + embed(ids),
+ * ids [B][S] with S = the sequence length vox_encode_audio would report; logits [B][S][vocab] host.  Leaves the
+ * decoder KV cache filled with the S positions.  (Parity/debug entry: it ships every logit to the host.) */
+int32_t vox_forward_streaming(vox_session *s, const float *mel, int32_t b, int32_t t_frames, const int32_t *ids,
+                              int32_t n_ids, float *logits, size_t cap_floats);
+/* Device-side incremental decode (the production form of generate_step_with_cache, model.rs:857-867: same graph, but
+ * the greedy argmax (model.rs:922, 957) stays on the device and feeds the next step instead of shipping
+ * [B][M][vocab] logits to the host).
+ * vox_prefill: ids [B][M] at cache positions len..len+M-1; add_audio != 0 adds the session's audio embeddings of
+ * those positions (after vox_encode_audio; model.rs:894-903); next_tok [B] (nullable) = argmax of the last row.
+ * vox_decode_step: one position; tok [B] NULL = use the device-side token left by the previous call;
+ * next_tok NULL with tok NULL = fully asynchronous (no host sync). */
+int32_t vox_prefill(vox_session *s, const int32_t *ids, int32_t b, int32_t m, int32_t add_audio, int32_t *next_tok);
+int32_t vox_decode_step(vox_session *s, const int32_t *tok /* nullable */, int32_t b, int32_t add_audio,
+                        int32_t *next_tok /* nullable */);
 int32_t vox_session_cache_len(const vox_session *s, int32_t *len);             /* LayerCaches::seq_len */
 int32_t vox_session_reset(vox_session *s);                                       /* LayerCaches::reset  */
 /* debugging / parity: copy an internal activation by name ("enc_out","audio_embeds","conv","enc<i>",

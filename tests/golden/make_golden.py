@@ -43,12 +43,12 @@ def tiny():
     print("tiny:", len(toks), "tokens, min margin", min(info["margins"]))
 
 
-def full(seconds=16.0, gguf="/dev/shm/voxtral_synth_s42.gguf"):
+def full(seconds=16.0, gguf="/dev/shm/voxtral_synth_s42.gguf", audio_seed=1234, out_name="full_s42_16s.npz"):
     cfg = gguf_synth.VoxtralConfig()
     t0 = time.time()
     if not os.path.exists(gguf):
         print(gguf_synth.write_synthetic_gguf(gguf, cfg, seed=42), f"{time.time() - t0:.1f}s")
-    audio = omel.speechlike(seconds, seed=1234)
+    audio = omel.speechlike(seconds, seed=audio_seed)
     mel = omel.mel_tensor_from_audio(omel.peak_normalize(audio))
     om = OracleModel(gguf)
     info = {}
@@ -59,7 +59,7 @@ def full(seconds=16.0, gguf="/dev/shm/voxtral_synth_s42.gguf"):
     toks = om.transcribe_streaming(mel, omel.time_embedding(6.0, cfg.dec_dim), audio_embeds=emb, info=info)
     print(f"oracle decode {time.time() - t0:.1f}s")
     e = emb.numpy().astype(np.float32)
-    np.savez_compressed(os.path.join(HERE, "full_s42_16s.npz"), tokens=np.array(toks, np.int32),
+    np.savez_compressed(os.path.join(HERE, out_name), audio_seed=np.int32(audio_seed), tokens=np.array(toks, np.int32),
                         margins=np.array(info["margins"], np.float32), second=np.array(info["second"], np.int32), rows=np.array(FULL_ROWS, np.int32),
                         audio_rows=e[FULL_ROWS], row_sums=e.astype(np.float64).sum(1),
                         row_abs_sums=np.abs(e).astype(np.float64).sum(1), seconds=np.float32(seconds))
@@ -68,6 +68,9 @@ def full(seconds=16.0, gguf="/dev/shm/voxtral_synth_s42.gguf"):
 
 
 if __name__ == "__main__":
-    tiny()
+    if "--no-tiny" not in sys.argv:
+        tiny()
     if "--full" in sys.argv:
         full()
+    if "--full2" in sys.argv:      # second utterance (different audio seed): one golden is thin
+        full(audio_seed=99, out_name="full_s42_16s_b.npz")

@@ -209,6 +209,68 @@ def test_generate_step_with_cache_parity(tiny_model, tiny_oracle):
     assert np.abs(a - b).max() > 1e-3
 
 
+def test_device_side_incremental_api(tiny_model, tiny_oracle):
+    """vox_prefill + vox_decode_step (model.rs:857-867 with the argmax kept on the device): driving the
+    decoder step by step reproduces transcribe_streaming, with device feedback (tok=None), with host-fed tokens,
+    batched, and without audio (== argmax of generate_step_with_cache's logits)."""
+    sigs = [omel.peak_normalize(omel.speechlike(4.0, 50 + i)) for i in range(3)]
+    mels = np.concatenate([omel.mel_tensor_from_audio(a) for a in sigs])
+    want = tiny_model.transcribe_streaming(mels)                  # [3, n]
+    n = want.shape[1]
+    t_embed = omel.time_embedding(6.0, tiny_oracle.cfg.dec_dim)
+    assert want[0].tolist() == tiny_oracle.transcribe_streaming(mels[:1], t_embed)
+    prefix = np.array([[1] + [32] * 37] * 3, np.int32)
+    # (a) device feedback, batched
+    tiny_model.encode_audio(mels)
+    tiny_model.reset_cache()
+    out = [tiny_model.prefill(prefix)]
+    for _ in range(n - 2):
+        tiny_model.decode_step(batch=3, read=False)               # fully asynchronous steps
+        out.append(None)
+    last = tiny_model.decode_step(batch=3)
+    assert tiny_model.cache_len() == 38 + n - 1
+    assert np.array_equal(out[0], want[:, 0]) and np.array_equal(last, want[:, n - 1])
+    # (b) host-fed tokens (teacher forcing with the known ids), single stream
+    tiny_model.encode_audio(mels[1:2])
+    tiny_model.reset_cache()
+    got = [int(tiny_model.prefill(prefix[:1])[0])]
+    for j in range(1, n):
+        got.append(int(tiny_model.decode_step(tok=[int(want[1, j - 1])])[0]))
+    assert got == want[1].tolist()
+    # (c) token-only (no audio): equals the argmax of generate_step_with_cache
+    ids = np.array([[1, 32, 77, 400, 9]], np.int32)
+    tiny_model.reset_cache()
+    lg = tiny_model.generate_step_with_cache(ids)
+    tiny_model.reset_cache()
+    nxt = tiny_model.prefill(ids, add_audio=False)
+    assert int(nxt[0]) == int(lg[0, -1].argmax())
+    lg2 = tiny_model.generate_step_with_cache(np.array([[int(nxt[0])]]))
+    tiny_model.reset_cache()
+    tiny_model.prefill(ids, add_audio=False)
+    assert int(tiny_model.decode_step(batch=1, add_audio=False)[0]) == int(lg2[0, 0].argmax())
+    # argument checking: audio positions exhausted / wrong batch
+    tiny_model.encode_audio(mels[:1])
+    tiny_model.reset_cache()
+    with pytest.raises(Exception, match="add_audio"):
+        tiny_model.prefill(prefix[:2])
+
+
+def test_forward_streaming_parity(tiny_model, tiny_oracle):
+    """forward_streaming (model.rs:801-814): teacher-forced logits for every position vs the oracle."""
+    _, mel = _mel(4.0, seed=9)
+    emb = tiny_oracle.encode_audio(mel)
+    s4 = emb.shape[0]
+    rng = np.random.default_rng(0)
+    ids = rng.integers(0, tiny_oracle.cfg.vocab, size=s4).astype(np.int32)
+    ids[0] = 1
+    exp = tiny_oracle.forward_streaming(mel, ids.tolist(), omel.time_embedding(6.0, tiny_oracle.cfg.dec_dim), audio_embeds=emb).numpy()
+    got = tiny_model.forward_streaming(mel, ids[None])[0]
+    assert got.shape == exp.shape
+    assert np.abs(got - exp).max() < 1e-3
+    assert np.array_equal(got.argmax(1), exp.argmax(1))
+    assert tiny_model.cache_len() == s4
+
+
 def test_set_delay_changes_ada(tiny_model, tiny_oracle):
     cfg = tiny_oracle.cfg
     for delay in (6.0, 2.0):

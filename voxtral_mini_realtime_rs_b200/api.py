@@ -126,6 +126,9 @@ _SIGS = {
     "vox_transcribe_pcm_dev": (C.c_int32, [_P, _P, C.c_int32, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_int32),
                                            C.POINTER(_Timings)]),
     "vox_generate_step_with_cache": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, C.c_size_t]),
+    "vox_forward_streaming": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_size_t]),
+    "vox_prefill": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "vox_decode_step": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P]),
     "vox_session_cache_len": (C.c_int32, [_P, C.POINTER(C.c_int32)]),
     "vox_session_reset": (C.c_int32, [_P]),
     "vox_session_debug_read": (C.c_int32, [_P, C.c_char_p, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -580,6 +583,42 @@ class Q4VoxtralModel:
         out = np.empty((b, m, self.info["vocab"]), np.float32)
         _check(lib().vox_generate_step_with_cache(self._s, _ptr(ids), b, m, _ptr(out), out.size))
         return out
+
+    def forward_streaming(self, mel, token_ids) -> np.ndarray:
+        """mel [B,128,T] (or [128,T]), ids [B,S] -> logits [B,S,vocab]: teacher-forced full pass with
+        inputs = audio_embeds + embed(ids) (model.rs:801-814)."""
+        mel = np.ascontiguousarray(mel, np.float32)
+        if mel.ndim == 2:
+            mel = mel[None]
+        ids = np.ascontiguousarray(token_ids, dtype=np.int32)
+        if ids.ndim == 1:
+            ids = ids[None]
+        b, _, t = mel.shape
+        assert ids.shape[0] == b
+        out = np.empty((b, ids.shape[1], self.info["vocab"]), np.float32)
+        _check(lib().vox_forward_streaming(self._s, _ptr(mel), b, t, _ptr(ids), ids.shape[1], _ptr(out), out.size))
+        return out
+
+    def prefill(self, token_ids, add_audio: bool = True) -> np.ndarray:
+        """ids [B,M] -> next token per stream [B]; greedy argmax on the device (vox_prefill)."""
+        ids = np.ascontiguousarray(token_ids, dtype=np.int32)
+        if ids.ndim == 1:
+            ids = ids[None]
+        b, m = ids.shape
+        nxt = np.empty(b, np.int32)
+        _check(lib().vox_prefill(self._s, _ptr(ids), b, m, int(add_audio), _ptr(nxt)))
+        return nxt
+
+    def decode_step(self, tok=None, batch: int | None = None, add_audio: bool = True, read: bool = True):
+        """One decode position.  tok None = device-side feedback of the previous call (vox_decode_step)."""
+        if tok is not None:
+            tok = np.ascontiguousarray(tok, dtype=np.int32).reshape(-1)
+            batch = tok.size
+        assert batch is not None
+        nxt = np.empty(batch, np.int32) if read else None
+        _check(lib().vox_decode_step(self._s, _ptr(tok) if tok is not None else None, batch, int(add_audio),
+                                     _ptr(nxt) if read else None))
+        return nxt
 
     def cache_len(self) -> int:
         v = C.c_int32()

@@ -655,6 +655,92 @@ int32_t vox_generate_step_with_cache(vox_session *sh, const int32_t *ids, int32_
     s->cache_len += m;
     VOX_API_END
 }
+// forward_streaming (model.rs:801-814): teacher-forced full pass, inputs = audio_embeds + embed(ids).
+int32_t vox_forward_streaming(vox_session *sh, const float *mel, int32_t b, int32_t t, const int32_t *ids, int32_t n_ids,
+                              float *logits, size_t cap) {
+    VOX_API_BEGIN
+    REQUIRE(sh); REQUIRE(mel); REQUIRE(ids); REQUIRE(logits);
+    Session *s = sh->s;
+    const vox_model_info &c = s->m->info;
+    upload_mel(s, mel, b, t);
+    s->encode(b, t);
+    const int S4 = s->cur_S4;
+    VOX_CHECK(n_ids == S4, VOX_EINVAL, "forward_streaming needs one token id per audio position (%d), got %d", S4, n_ids);
+    VOX_CHECK(S4 <= s->out_ld, VOX_EINVAL, "sequence %d exceeds the session KV capacity %d", S4, s->out_ld);
+    for (int i = 0; i < b * n_ids; ++i) VOX_CHECK(ids[i] >= 0 && ids[i] < c.vocab, VOX_EINVAL, "token id %d out of range", ids[i]);
+    const size_t n = (size_t)b * S4 * c.vocab;
+    VOX_CHECK(cap >= n, VOX_ECAPACITY, "logits capacity %zu < %zu", cap, n);
+    s->reset();
+    const int Mc = s->M_max;
+    const size_t chunk_floats = (size_t)b * Mc * c.vocab;
+    if (chunk_floats > s->logits_all_cap) {
+        s->logits_all = s->arena.alloc_n<float>(chunk_floats);
+        s->logits_all_cap = chunk_floats;
+    }
+    std::vector<int> chunk_ids;
+    for (int p0 = 0; p0 < S4; p0 += Mc) {
+        const int m = std::min(Mc, S4 - p0);
+        chunk_ids.resize((size_t)b * m);
+        for (int bb = 0; bb < b; ++bb)
+            for (int i = 0; i < m; ++i) chunk_ids[(size_t)bb * m + i] = ids[(size_t)bb * S4 + p0 + i];
+        CUDA_OK(cudaMemcpyAsync(s->d_ids, chunk_ids.data(), sizeof(int) * chunk_ids.size(), cudaMemcpyHostToDevice, s->st));
+        launch_embed(s->m->tok_emb, s->d_ids, s->audio, S4, b, m, s->d_pos, s->x_dec, s->fused_decode(b * m) ? s->ssq_x : nullptr, s->st);
+        const bool pending = s->decoder_forward(b, m);
+        s->lm_head_rows(b * m, pending, s->logits_all);
+        launch_advance(s->d_pos, m, nullptr, 0, s->st);
+        for (int bb = 0; bb < b; ++bb)
+            CUDA_OK(cudaMemcpyAsync(logits + ((size_t)bb * S4 + p0) * c.vocab, s->logits_all + (size_t)bb * m * c.vocab,
+                                    sizeof(float) * (size_t)m * c.vocab, cudaMemcpyDeviceToHost, s->st));
+        CUDA_OK(cudaStreamSynchronize(s->st));  // chunk_ids is reused
+    }
+    s->cache_len = S4;
+    VOX_API_END
+}
+
+// Device-side incremental decode (model.rs:857-867 without the logits round trip): the argmax stays on
+// the device and feeds the next step; only b int32 ids cross the bus, and only when the caller asks for them.
+int32_t vox_prefill(vox_session *sh, const int32_t *ids, int32_t b, int32_t m, int32_t add_audio, int32_t *next_tok) {
+    VOX_API_BEGIN
+    REQUIRE(sh); REQUIRE(ids);
+    Session *s = sh->s;
+    const vox_model_info &c = s->m->info;
+    VOX_CHECK(b >= 1 && b <= s->max_batch, VOX_EINVAL, "batch %d exceeds session max_batch %d", b, s->max_batch);
+    VOX_CHECK(m >= 1 && m <= s->M_max, VOX_EINVAL, "M=%d out of range [1,%d]", m, s->M_max);
+    VOX_CHECK(s->cache_len + m <= s->out_ld, VOX_EINVAL, "KV cache full (%d + %d > %d)", s->cache_len, m, s->out_ld);
+    if (add_audio)
+        VOX_CHECK(b == s->cur_B && s->cache_len + m <= s->cur_S4, VOX_EINVAL,
+                  "add_audio: positions %d..%d need audio embeddings of %d streams (have %d positions for %d streams; call vox_encode_audio first)",
+                  s->cache_len, s->cache_len + m, b, s->cur_S4, s->cur_B);
+    for (int i = 0; i < b * m; ++i) VOX_CHECK(ids[i] >= 0 && ids[i] < c.vocab, VOX_EINVAL, "token id %d out of range", ids[i]);
+    CUDA_OK(cudaSetDevice(s->m->device));
+    s->prefill(b, m, ids, add_audio != 0);
+    s->cache_len += m;
+    if (next_tok) CUDA_OK(cudaMemcpyAsync(next_tok, s->d_tok, sizeof(int) * b, cudaMemcpyDeviceToHost, s->st));
+    CUDA_OK(cudaStreamSynchronize(s->st));   // `ids` is caller memory
+    VOX_API_END
+}
+int32_t vox_decode_step(vox_session *sh, const int32_t *tok, int32_t b, int32_t add_audio, int32_t *next_tok) {
+    VOX_API_BEGIN
+    REQUIRE(sh);
+    Session *s = sh->s;
+    const vox_model_info &c = s->m->info;
+    VOX_CHECK(b >= 1 && b <= s->max_batch, VOX_EINVAL, "batch %d exceeds session max_batch %d", b, s->max_batch);
+    VOX_CHECK(s->cache_len + 1 <= s->out_ld, VOX_EINVAL, "KV cache full (%d + 1 > %d)", s->cache_len, s->out_ld);
+    if (add_audio)
+        VOX_CHECK(b == s->cur_B && s->cache_len < s->cur_S4, VOX_EINVAL,
+                  "add_audio: position %d has no audio embedding (%d positions, %d streams encoded)", s->cache_len, s->cur_S4, s->cur_B);
+    CUDA_OK(cudaSetDevice(s->m->device));
+    if (tok) {
+        for (int i = 0; i < b; ++i) VOX_CHECK(tok[i] >= 0 && tok[i] < c.vocab, VOX_EINVAL, "token id %d out of range", tok[i]);
+        CUDA_OK(cudaMemcpyAsync(s->d_tok, tok, sizeof(int) * b, cudaMemcpyHostToDevice, s->st));
+    }
+    s->decode_step(b, add_audio != 0);
+    s->mega_steps_host += 1;
+    s->cache_len += 1;
+    if (next_tok) CUDA_OK(cudaMemcpyAsync(next_tok, s->d_tok, sizeof(int) * b, cudaMemcpyDeviceToHost, s->st));
+    if (next_tok || tok) CUDA_OK(cudaStreamSynchronize(s->st));
+    VOX_API_END
+}
 int32_t vox_session_cache_len(const vox_session *s, int32_t *len) {
     VOX_API_BEGIN
     REQUIRE(s); REQUIRE(len);

@@ -191,7 +191,9 @@ __device__ __forceinline__ float4 mul4(const float4 a, const float4 b) { return 
 
 // Activation fragments of one 32-element block for one token (same encoding as matvec_tc.cu tc_stage):
 //   bf_blk  : uint2  [2 (nibble half j)][2*MT cols][4 t]   B fragments {b0,b1} of lane (g = col, t);
-//             column 2*m = f16 hi piece of token m, 2*m+1 = mid piece
+//             column 2*m = f16 hi piece of token m, 2*m+1 = mid piece            (MT <= 4)
+//             uint2  [2 (piece: hi, mid)][32 lanes = (token m, t)][2 (nibble half j)]   (MT == 8: the columns of
+//             the MMA are the 8 tokens; hi and mid pieces are chained into one accumulator)
 //   off_blk : float2 [MT]   { -8 * sum_{k in block} x , 2^24 / block scale }
 // One work item = (token m, t): elements 4t..4t+3 (l) and 16+4t..16+4t+3 (h) of the block, already
 // multiplied by the consumer's norm weight.  The four t-items of a block must sit in four adjacent
@@ -229,11 +231,94 @@ __device__ __forceinline__ void frag_build(const float4 l, const float4 h, const
         fh.y = pack_h2(hh[o + 1], hh[o + 3]);
         fm.x = pack_h2(md[o + 0], md[o + 2]);
         fm.y = pack_h2(md[o + 1], md[o + 3]);
-        uint2 *dst = bf_blk + (size_t)j * (2 * MT) * 4;
-        dst[(2 * m + 0) * 4 + t] = fh;
-        dst[(2 * m + 1) * 4 + t] = fm;
+        if constexpr (MT == 8) {
+            // token-column layout: [piece p][lane = m*4+t][j] -- a consumer lane (g = token, t) fetches its hi pieces of
+            // both nibble halves with one 128-bit load and its mid pieces with another (no bank conflicts)
+            bf_blk[((0 * 32 + m * 4 + t) * 2) + j] = fh;
+            bf_blk[((1 * 32 + m * 4 + t) * 2) + j] = fm;
+        } else {
+            uint2 *dst = bf_blk + (size_t)j * (2 * MT) * 4;
+            dst[(2 * m + 0) * 4 + t] = fh;
+            dst[(2 * m + 1) * 4 + t] = fm;
+        }
     }
     if (t == 0) off_blk[m] = make_float2(-8.0f * bs, inv);
+}
+
+// One block pair (64 k) of NTV tiles against the activation fragments: the arithmetic of matvec_tc.cu.  The nibbles of
+// the two blocks enter m16n8k16 as f16 subnormals (low nibbles n * 2^-24, high nibbles n * 2^-20, whose activation
+// pieces are pre-scaled by 1/16); the f32 block sum is scaled by 2^24 / (block scale), offset by -8 * sum(x) and
+// multiplied by the row's f16 scale d.
+//   MT <= 4: MMA columns = (token, piece) pairs; hi and mid land in neighbouring columns and are added in f32.
+//   MT == 8: MMA columns = the 8 tokens; the hi and mid pieces of both nibble halves are chained into ONE accumulator
+//            (4 MMAs per block and tile, 2 FFMA per output): each lane finishes rows g, g+8 x tokens 2t, 2t+1.
+template <int MT, int NT, int NTV>
+__device__ __forceinline__ void mg_pair(const unsigned char *__restrict__ sb, const uint32_t slot_q, const uint32_t slot_d,
+                                        const uint2 *__restrict__ bfp, const float2 *__restrict__ ofp, const int g, const int t,
+                                        const int lane, float (&acc)[NT][2 * ((MT + 3) / 4)]) {
+    constexpr int CG = (MT + 3) / 4;
+    uint4 wq[NTV];
+    uint2 wd[NTV];
+#pragma unroll
+    for (int u = 0; u < NTV; ++u) {
+        wq[u] = *reinterpret_cast<const uint4 *>(sb + (size_t)u * MG_SLOT_BYTES + slot_q);
+        wd[u] = *reinterpret_cast<const uint2 *>(sb + (size_t)u * MG_SLOT_BYTES + slot_d);
+    }
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb) {
+        if constexpr (MT == 8) {
+            const uint4 *bq = reinterpret_cast<const uint4 *>(bfp + (size_t)bb * (16 * MT));
+            const uint4 fh = bq[lane], fm = bq[32 + lane];  // {b0,b1} of the low-nibble half, {b0,b1} of the high-nibble half
+            const float4 o = *reinterpret_cast<const float4 *>(ofp + bb * MT + 2 * t);  // {off, inv} of tokens 2t, 2t+1
+#pragma unroll
+            for (int u = 0; u < NTV; ++u) {
+                const uint32_t wg = bb ? wq[u].z : wq[u].x, wg8 = bb ? wq[u].w : wq[u].y;
+                const uint32_t dw = bb ? wd[u].y : wd[u].x;
+                const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&dw));
+                const uint32_t sg = wg >> 8, sg8 = wg8 >> 8;
+                float cc[4] = {0.f, 0.f, 0.f, 0.f};
+                mma16816(cc, wg & 0x000F000Fu, wg8 & 0x000F000Fu, sg & 0x000F000Fu, sg8 & 0x000F000Fu, fh.x, fh.y);
+                mma16816(cc, wg & 0x00F000F0u, wg8 & 0x00F000F0u, sg & 0x00F000F0u, sg8 & 0x00F000F0u, fh.z, fh.w);
+                mma16816(cc, wg & 0x000F000Fu, wg8 & 0x000F000Fu, sg & 0x000F000Fu, sg8 & 0x000F000Fu, fm.x, fm.y);
+                mma16816(cc, wg & 0x00F000F0u, wg8 & 0x00F000F0u, sg & 0x00F000F0u, sg8 & 0x00F000F0u, fm.z, fm.w);
+                acc[u][0] = fmaf(d.x, fmaf(cc[0], o.y, o.x), acc[u][0]);
+                acc[u][1] = fmaf(d.x, fmaf(cc[1], o.w, o.z), acc[u][1]);
+                acc[u][2] = fmaf(d.y, fmaf(cc[2], o.y, o.x), acc[u][2]);
+                acc[u][3] = fmaf(d.y, fmaf(cc[3], o.w, o.z), acc[u][3]);
+            }
+        } else {
+            const uint2 *bfb = bfp + (size_t)(bb * 2) * (2 * MT) * 4;
+            uint2 blo[CG], bhi[CG];
+            float2 of[CG];
+#pragma unroll
+            for (int c = 0; c < CG; ++c) {
+                const int col = c * 8 + g;
+                blo[c] = make_uint2(0u, 0u);
+                bhi[c] = blo[c];
+                if (col < 2 * MT) {
+                    blo[c] = bfb[col * 4 + t];
+                    bhi[c] = bfb[(2 * MT + col) * 4 + t];
+                }
+                const int tok = c * 4 + t;
+                of[c] = tok < MT ? ofp[bb * MT + tok] : make_float2(0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < NTV; ++u) {
+                const uint32_t wg = bb ? wq[u].z : wq[u].x, wg8 = bb ? wq[u].w : wq[u].y;
+                const uint32_t dw = bb ? wd[u].y : wd[u].x;
+                const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&dw));
+                const uint32_t sg = wg >> 8, sg8 = wg8 >> 8;
+#pragma unroll
+                for (int c = 0; c < CG; ++c) {
+                    float cc[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma16816(cc, wg & 0x000F000Fu, wg8 & 0x000F000Fu, sg & 0x000F000Fu, sg8 & 0x000F000Fu, blo[c].x, blo[c].y);
+                    mma16816(cc, wg & 0x00F000F0u, wg8 & 0x00F000F0u, sg & 0x00F000F0u, sg8 & 0x00F000F0u, bhi[c].x, bhi[c].y);
+                    acc[u][2 * c] = fmaf(d.x, fmaf(cc[0] + cc[1], of[c].y, of[c].x), acc[u][2 * c]);
+                    acc[u][2 * c + 1] = fmaf(d.y, fmaf(cc[2] + cc[3], of[c].y, of[c].x), acc[u][2 * c + 1]);
+                }
+            }
+        }
+    }
 }
 
 template <int MT, int G, int DPL>
@@ -421,11 +506,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                     // share one read of the activation fragments
                     for (int it = 0; it < ntl; it += NT) {
                         const int nt = min(NT, ntl - it);
-                        float acc[NT][CG][2];
+                        float acc[NT][2 * CG];
 #pragma unroll
                         for (int u = 0; u < NT; ++u)
 #pragma unroll
-                            for (int c = 0; c < CG; ++c) acc[u][c][0] = acc[u][c][1] = 0.0f;
+                            for (int c = 0; c < 2 * CG; ++c) acc[u][c] = 0.0f;
                         // reducer threads: (tile slot, token, row) = (tid / 16MT, (tid % 16MT) / 16, tid % 16)
                         const int r_slot = tid / (16 * MT), r_tok = (tid % (16 * MT)) >> 4, r_r = tid & 15;
                         const int r_tile = mg_tile_of(it + r_slot, UT, cta, nctas);
@@ -447,67 +532,31 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                             fg_lo = *reinterpret_cast<const float4 *>(fout_gamma + (size_t)f_blk * 32 + 4 * bt);
                             fg_hi = *reinterpret_cast<const float4 *>(fout_gamma + (size_t)f_blk * 32 + 16 + 4 * bt);
                         }
-                        for (int c0 = 0; c0 < np; c0 += MG_CHUNK) {
-                            mbar_wait(&full[stage], phase, wd_flag, 0x200u + (unsigned)oi);
-                            if (tracing && s == 0 && it == 0 && c0 == 0) p.trace[oi * 6 + 4] = (unsigned long long)clock64();
-                            const int pp = c0 + warp;  // pair index inside the slice
-                            if (pp < np) {
-                                const unsigned char *sb = ring + (size_t)stage * (NT * MG_SLOT_BYTES);
-                                uint4 wq[NT];
-                                uint2 wd[NT];
-#pragma unroll
-                                for (int u = 0; u < NT; ++u) {
-                                    if (u < nt) {
-                                        wq[u] = reinterpret_cast<const uint4 *>(sb + (size_t)u * MG_SLOT_BYTES)[warp * 32 + lane];
-                                        wd[u] = reinterpret_cast<const uint2 *>(sb + (size_t)u * MG_SLOT_BYTES + MG_SLOT_Q)[warp * 8 + g];
-                                    }
+                        // ---- the weight loop: one block pair per warp per ring stage, for the group's nt tiles.
+                        // Guard-free bodies (nt is warp-uniform: one instantiation per count; a warp without a pair in
+                        // a ragged last chunk only recycles the stage).
+                        {
+                            const uint32_t slot_q = (uint32_t)warp * 512u + (uint32_t)lane * 16u;
+                            const uint32_t slot_d = (uint32_t)MG_SLOT_Q + (uint32_t)warp * 64u + (uint32_t)g * 8u;
+                            for (int c0 = 0; c0 < np; c0 += MG_CHUNK) {
+                                mbar_wait(&full[stage], phase, wd_flag, 0x200u + (unsigned)oi);
+                                if (tracing && s == 0 && it == 0 && c0 == 0) p.trace[oi * 6 + 4] = (unsigned long long)clock64();
+                                const int pp = c0 + warp;  // pair index inside the slice
+                                if (pp < np) {
+                                    const unsigned char *sb = ring + (size_t)stage * (NT * MG_SLOT_BYTES);
+                                    const uint2 *bfp = bf + (size_t)pp * (2 * 16 * MT);
+                                    const float2 *ofp = off2 + (size_t)pp * (2 * MT);
+                                    if (nt == NT) mg_pair<MT, NT, NT>(sb, slot_q, slot_d, bfp, ofp, g, t, lane, acc);
+                                    else if (NT > 1 && nt == 1) mg_pair<MT, NT, 1>(sb, slot_q, slot_d, bfp, ofp, g, t, lane, acc);
+                                    else if (NT > 2 && nt == 2) mg_pair<MT, NT, 2>(sb, slot_q, slot_d, bfp, ofp, g, t, lane, acc);
+                                    else if (NT > 3 && nt == 3) mg_pair<MT, NT, 3>(sb, slot_q, slot_d, bfp, ofp, g, t, lane, acc);
                                 }
-#pragma unroll
-                                for (int bb = 0; bb < 2; ++bb) {
-                                    const int bl = pp * 2 + bb;
-                                    const uint2 *bfb = bf + (size_t)(bl * 2) * (2 * MT) * 4;
-                                    uint2 blo[CG], bhi[CG];
-                                    float2 of[CG];
-#pragma unroll
-                                    for (int c = 0; c < CG; ++c) {
-                                        const int col = c * 8 + g;
-                                        blo[c] = make_uint2(0u, 0u);
-                                        bhi[c] = blo[c];
-                                        if (col < 2 * MT) {
-                                            blo[c] = bfb[col * 4 + t];
-                                            bhi[c] = bfb[(2 * MT + col) * 4 + t];
-                                        }
-                                        const int tok = c * 4 + t;
-                                        of[c] = tok < MT ? off2[bl * MT + tok] : make_float2(0.0f, 0.0f);
-                                    }
-#pragma unroll
-                                    for (int u = 0; u < NT; ++u) {
-                                        if (u < nt) {
-                                            const uint32_t wg = bb ? wq[u].z : wq[u].x, wg8 = bb ? wq[u].w : wq[u].y;
-                                            const uint32_t dw = bb ? wd[u].y : wd[u].x;
-                                            const __half2 dh = *reinterpret_cast<const __half2 *>(&dw);
-                                            const float d0 = __low2float(dh), d1 = __high2float(dh);
-                                            const uint32_t sg = wg >> 8, sg8 = wg8 >> 8;
-                                            const uint32_t a_lo[4] = {wg & 0x000F000Fu, wg8 & 0x000F000Fu, sg & 0x000F000Fu, sg8 & 0x000F000Fu};
-                                            const uint32_t a_hi[4] = {wg & 0x00F000F0u, wg8 & 0x00F000F0u, sg & 0x00F000F0u, sg8 & 0x00F000F0u};
-#pragma unroll
-                                            for (int c = 0; c < CG; ++c) {
-                                                // low and high nibbles accumulate into one tile (the NT tiles give the ILP)
-                                                float cc[4] = {0.f, 0.f, 0.f, 0.f};
-                                                mma16816(cc, a_lo[0], a_lo[1], a_lo[2], a_lo[3], blo[c].x, blo[c].y);
-                                                mma16816(cc, a_hi[0], a_hi[1], a_hi[2], a_hi[3], bhi[c].x, bhi[c].y);
-                                                acc[u][c][0] = fmaf(d0, fmaf(cc[0] + cc[1], of[c].y, of[c].x), acc[u][c][0]);
-                                                acc[u][c][1] = fmaf(d1, fmaf(cc[2] + cc[3], of[c].y, of[c].x), acc[u][c][1]);
-                                            }
-                                        }
-                                    }
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&empty[stage]);
+                                if (++stage == nstage) {
+                                    stage = 0;
+                                    phase ^= 1u;
                                 }
-                            }
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&empty[stage]);
-                            if (++stage == nstage) {
-                                stage = 0;
-                                phase ^= 1u;
                             }
                         }
                         if (tracing && s + 1 == S && it + NT >= ntl) p.trace[oi * 6 + 5] = (unsigned long long)clock64();
@@ -516,12 +565,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
 #pragma unroll
                         for (int u = 0; u < NT; ++u) {
                             if (u < nt) {
+                                if constexpr (MT == 8) {  // lane (g, t): rows g, g+8 x tokens 2t, 2t+1
+                                    rw[(u * MT + 2 * t) * 16 + g] = acc[u][0];
+                                    rw[(u * MT + 2 * t + 1) * 16 + g] = acc[u][1];
+                                    rw[(u * MT + 2 * t) * 16 + g + 8] = acc[u][2];
+                                    rw[(u * MT + 2 * t + 1) * 16 + g + 8] = acc[u][3];
+                                } else {
 #pragma unroll
-                                for (int c = 0; c < CG; ++c) {
-                                    const int tok = c * 4 + t;
-                                    if (tok < MT) {
-                                        rw[(u * MT + tok) * 16 + g] = acc[u][c][0];
-                                        rw[(u * MT + tok) * 16 + g + 8] = acc[u][c][1];
+                                    for (int c = 0; c < CG; ++c) {
+                                        const int tok = c * 4 + t;
+                                        if (tok < MT) {
+                                            rw[(u * MT + tok) * 16 + g] = acc[u][2 * c];
+                                            rw[(u * MT + tok) * 16 + g + 8] = acc[u][2 * c + 1];
+                                        }
                                     }
                                 }
                             }

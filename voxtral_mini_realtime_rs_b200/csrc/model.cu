@@ -808,7 +808,7 @@ bool Session::mega_prepare(int B) {
 
 // One autoregressive step for B streams (model.rs:938-960): embed(prev token) + audio[pos-1],
 // 26 layers, lm_head, argmax, device-side feedback; all positions read from device counters.
-void Session::decode_step(int B) {
+void Session::decode_step(int B, bool add_audio) {
     const vox_model_info &c = m->info;
     if (mega_prepare(B)) {
         MegaParams p;
@@ -839,7 +839,7 @@ void Session::decode_step(int B) {
         p.emb_qs = m->tok_emb.qs;
         p.emb_d = m->tok_emb.d;
         p.D = c.dec_dim;
-        p.audio = audio;
+        p.audio = add_audio ? audio : nullptr;
         p.audio_seq = cur_S4;
         p.x_dec = x_dec;
         p.ssq_x = ssq_x;
@@ -866,11 +866,27 @@ void Session::decode_step(int B) {
         launch_decode_mega(p, mega_plan, mega_grid, st);
         return;
     }
-    launch_embed(m->tok_emb, d_tok, audio, cur_S4, B, 1, d_pos, x_dec, fused_decode(B) ? ssq_x : nullptr, st);
+    launch_embed(m->tok_emb, d_tok, add_audio ? audio : nullptr, cur_S4, B, 1, d_pos, x_dec, fused_decode(B) ? ssq_x : nullptr, st);
     const bool pending = decoder_forward(B, 1);
     lm_head_rows(B, pending, logits);
     launch_argmax_multi(logits, B, c.vocab, d_tok, d_out, out_ld, d_outpos, am_vals, am_idx, am_cnt, st);
     launch_advance(d_pos, 1, d_outpos, 1, st);
+}
+
+// Prefill of M positions for B streams (model.rs:894-923 with M = 38; also the incremental vox_prefill).
+void Session::prefill(int B, int M, const int *ids_host, bool add_audio) {
+    const vox_model_info &c = m->info;
+    CUDA_OK(cudaMemcpyAsync(d_ids, ids_host, sizeof(int) * (size_t)B * M, cudaMemcpyHostToDevice, st));
+    launch_embed(m->tok_emb, d_ids, add_audio ? audio : nullptr, cur_S4, B, M, d_pos, x_dec, fused_decode(B * M) ? ssq_x : nullptr, st);
+    const bool pending = decoder_forward(B, M);
+    if (pending) {   // decode-sized prefill (B*M <= 8): final norm still pending in x_dec
+        launch_rmsnorm(x_dec, m->dec_norm, nullptr, h_dec, B * M, c.dec_dim, m->norm_eps, st);
+    }
+    // lm_head on the last row only (the reference computes all M rows and keeps one)
+    launch_gather_last(h_dec, last_h, B, M, c.dec_dim, st);
+    linear(m->tok_emb, last_h, B, logits, c.vocab, nullptr, nullptr, EPI_NONE);
+    launch_argmax(logits, B, c.vocab, d_tok, d_out, out_ld, d_outpos, st);
+    launch_advance(d_pos, M, d_outpos, 1, st);
 }
 
 void Session::reset() {
@@ -902,14 +918,7 @@ int Session::transcribe_from_mel(int B, int T, int32_t *out_ids, size_t cap_ids,
         // prefix = [BOS] + [STREAMING_PAD]*37 (model.rs:883-892)
         std::vector<int> prefix((size_t)B * P, 32);
         for (int b = 0; b < B; ++b) prefix[(size_t)b * P] = 1;
-        CUDA_OK(cudaMemcpyAsync(d_ids, prefix.data(), sizeof(int) * prefix.size(), cudaMemcpyHostToDevice, st));
-        launch_embed(m->tok_emb, d_ids, audio, S4, B, P, d_pos, x_dec, fused_decode(B * P) ? ssq_x : nullptr, st);
-        decoder_forward(B, P);
-        // lm_head on the last prefix row only (the reference computes all 38 rows and keeps one)
-        launch_gather_last(h_dec, last_h, B, P, c.dec_dim, st);
-        linear(m->tok_emb, last_h, B, logits, c.vocab, nullptr, nullptr, EPI_NONE);
-        launch_argmax(logits, B, c.vocab, d_tok, d_out, out_ld, d_outpos, st);
-        launch_advance(d_pos, P, d_outpos, 1, st);
+        prefill(B, P, prefix.data(), true);
         CUDA_OK(cudaEventRecord(ev[4], st));
         const int steps = S4 - P - 1;
         if (steps > 0) mega_steps_host += (unsigned)steps;  // upper bound of the device epoch's advance

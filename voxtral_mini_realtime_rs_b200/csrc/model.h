@@ -167,7 +167,10 @@ struct Session {
                 int epi);
     bool decoder_forward(int B, int M);
     void lm_head_rows(int rows, bool norm_pending, float *dst);
-    void decode_step(int B);
+    void decode_step(int B, bool add_audio = true);
+    // generic prefill over ids [B][M] at positions *d_pos.. (+ audio rows when add_audio): KV append, lm_head of the
+    // last row, argmax -> d_tok (device feedback) and d_out; advances the counters
+    void prefill(int B, int M, const int *ids_host, bool add_audio);
     // runs prefill + loop; returns tokens per stream
     int transcribe_from_mel(int B, int T, int32_t *out_ids, size_t cap_ids, vox_timings *tm, bool timed_pre);
     void reset();
