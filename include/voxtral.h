@@ -217,6 +217,33 @@ int32_t vox_session_debug_read(vox_session *s, const char *what, float *out, siz
 int32_t vox_session_launch_count(const vox_session *s, uint64_t *launches);
 void vox_session_free(vox_session *s);
 
+/* ------------------------------------------------------------------ streaming sessions
+ * The reference has the pieces (Q4AudioEncoder::forward_with_cache model.rs:437-452, encode_audio_with_cache
+ * model.rs:790-799, KVCache::apply_sliding_window kv_cache.rs:176-203) but its CLI transcribes whole utterances.
+ * A pool is one GPU worker for up to max_sessions live sessions: audio is pushed in arbitrary pieces, vox_stream_tick
+ * advances every session as far as its audio allows -- incremental log-mel, conv stem with carried frames, encoder
+ * layers over per-layer K/V rings (absolute positions; keys older than the sliding window are overwritten), adapter,
+ * and ONE batched decoder step for all sessions that can take one (rows at different positions, paged KV) -- and
+ * every token is available as soon as its inputs are final.  The ids equal vox_transcribe_pcm's of the same audio.
+ * Samples must already be peak-normalised if the caller wants io.rs:59-68 semantics (it needs the whole utterance). */
+typedef struct vox_stream_pool vox_stream_pool;
+typedef struct {
+    float gpu_ms;            /* device time of the tick (CUDA events)                 */
+    int32_t live_sessions;   /* open and not yet drained after the tick               */
+    int32_t mel_frames, encoder_rows, prefills, decode_steps, decode_rows;
+} vox_stream_stats;
+int32_t vox_stream_pool_create(vox_model *m, int32_t max_sessions, float max_seconds, vox_stream_pool **out);
+int32_t vox_stream_open(vox_stream_pool *p, int32_t *session);
+int32_t vox_stream_push_pcm(vox_stream_pool *p, int32_t session, const float *samples, size_t n);
+int32_t vox_stream_finish(vox_stream_pool *p, int32_t session);        /* end of utterance: right padding, pad.rs:89-103 */
+int32_t vox_stream_tick(vox_stream_pool *p, vox_stream_stats *stats /* nullable */);
+/* ids emitted since the last poll; *done != 0 once the finished session has emitted everything */
+int32_t vox_stream_poll_ids(vox_stream_pool *p, int32_t session, int32_t *ids, size_t cap, size_t *n, int32_t *done);
+/* parity/debug: audio embeddings produced so far, [n][dec_dim] host */
+int32_t vox_stream_audio_embeds(vox_stream_pool *p, int32_t session, float *out, size_t cap_floats, int32_t *n);
+int32_t vox_stream_close(vox_stream_pool *p, int32_t session);
+void vox_stream_pool_free(vox_stream_pool *p);
+
 /* ------------------------------------------------------------------ tokenizer (host)
  * VoxtralTokenizer, src/tokenizer/mod.rs:70-214 */
 typedef struct vox_tokenizer vox_tokenizer;

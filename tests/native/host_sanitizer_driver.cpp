@@ -2,6 +2,7 @@
 // (GGUF reader over files and shards, Tekken tokenizer with its own JSON / base64 / UTF-8 code, audio plumbing):
 // well-formed inputs, truncations at many offsets and byte flips.  Malformed inputs must be rejected with vox::Error or
 // decoded harmlessly -- never a memory error.  Built and run by tests/test_host_sanitizers.py (no GPU).
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -43,6 +44,40 @@ int main(int argc, char** argv){
         try { Gguf* s = Gguf::open_shards(bufs, lens, 1); delete s; ++accepted; } catch (const Error&) { ++rejected; } catch (const std::exception&) { ++rejected; }
     }
     printf("gguf fuzz: %d rejected, %d accepted\n", rejected, accepted);
+    { // crafted index entries: offsets near 2^64, overflowing dims, deeply nested metadata arrays
+        auto put = [](std::string& b, const void* v, size_t n){ b.append((const char*)v, n); };
+        auto u32 = [&](std::string& b, uint32_t v){ put(b, &v, 4); };
+        auto u64 = [&](std::string& b, uint64_t v){ put(b, &v, 8); };
+        auto str = [&](std::string& b, const char* s){ u64(b, strlen(s)); b.append(s); };
+        auto craft = [&](uint64_t off, uint64_t d0, uint64_t d1, uint32_t dtype, int nest){
+            std::string b; u32(b, 0x46554747u); u32(b, 3); u64(b, 1); u64(b, nest ? 1 : 0);
+            if (nest) { str(b, "k"); u32(b, 9); for (int i = 0; i < nest; ++i) { u32(b, 9); u64(b, 1); } u32(b, 4); u64(b, 1); u32(b, 7); }
+            str(b, "t"); u32(b, 2); u64(b, d0); u64(b, d1); u32(b, dtype); u64(b, off);
+            b.append(256, '\0');
+            return b;
+        };
+        int bad_ok = 0, bad_rej = 0;
+        const uint64_t M = ~0ull;
+        std::vector<std::string> cases = { craft(M - 8, 4, 4, 0, 0), craft(M, 32, 1, 2, 0), craft(0, M / 2, 4, 0, 0), craft(0, 1ull << 33, 1ull << 33, 1, 0),
+                                           craft(64, 1ull << 62, 8, 2, 0), craft(0, 4, 4, 0, 1000), craft(1ull << 63, 4, 4, 0, 0), craft(0, 33, 1, 2, 0) };
+        for (auto& c : cases) {
+            const void* bufs[1] = {c.data()}; size_t lens[1] = {c.size()};
+            try { Gguf* s = Gguf::open_shards(bufs, lens, 1);
+                  for (auto& n : s->names()){ const GgufTensorInfo* t=s->find(n); std::vector<uint8_t> buf((size_t)std::min<uint64_t>(t->byte_size(), 1u << 20)); s->read_tensor(*t, buf.data()); }
+                  delete s; ++bad_ok; }
+            catch (const Error&) { ++bad_rej; }
+        }
+        printf("gguf crafted: %d rejected, %d accepted\n", bad_rej, bad_ok);
+        if (bad_ok != 0) { fprintf(stderr, "crafted GGUF accepted\n"); return 1; }
+    }
+    { // tokenizer: deep nesting and an unterminated trailing number must be errors, not crashes
+        std::string deep(100000, '['); int rej = 0;
+        try { Tokenizer* x = Tokenizer::from_json(deep.data(), deep.size()); delete x; } catch (const Error&) { ++rej; } catch (const std::exception&) { ++rej; }
+        std::vector<char> num = {'{','"','a','"',':','1','2','3','4','5'};   // exactly-sized heap buffer, no terminator
+        try { Tokenizer* x = Tokenizer::from_json(num.data(), num.size()); delete x; } catch (const Error&) { ++rej; } catch (const std::exception&) { ++rej; }
+        printf("tokenizer crafted: %d rejected\n", rej);
+        if (rej != 2) return 1;
+    }
     // ---- tokenizer: good file, truncations, byte flips
     std::string tj = slurp(tok_path);
     Tokenizer* t = Tokenizer::from_json(tj.data(), tj.size());

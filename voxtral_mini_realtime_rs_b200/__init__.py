@@ -17,12 +17,12 @@ from .api import (  # noqa: F401
     VoxtralError, lib, lib_path, device_count,
     GgufReader, Q4ModelLoader, Q4VoxtralModel, Q4Tensor, Q4Linear, q4_matmul,
     MelSpectrogram, PadConfig, pad_audio, peak_normalize, chunk_audio, needs_chunking, stream_progress,
-    TimeEmbedding, VoxtralTokenizer, Timings, DeviceBuffer, PinnedArray, q4_matmul_bench,
+    TimeEmbedding, VoxtralTokenizer, Timings, DeviceBuffer, PinnedArray, q4_matmul_bench, StreamingPool,
 )
 
 __all__ = [
     "VoxtralError", "lib", "lib_path", "device_count", "GgufReader", "Q4ModelLoader", "Q4VoxtralModel",
     "Q4Tensor", "Q4Linear", "q4_matmul", "MelSpectrogram", "PadConfig", "pad_audio", "peak_normalize",
     "chunk_audio", "needs_chunking", "stream_progress", "TimeEmbedding", "VoxtralTokenizer", "Timings", "DeviceBuffer",
-    "q4_matmul_bench", "PinnedArray",
+    "q4_matmul_bench", "PinnedArray", "StreamingPool",
 ]

@@ -134,6 +134,15 @@ _SIGS = {
     "vox_session_debug_read": (C.c_int32, [_P, C.c_char_p, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "vox_session_launch_count": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "vox_session_free": (None, [_P]),
+    "vox_stream_pool_create": (C.c_int32, [_P, C.c_int32, C.c_float, C.POINTER(_P)]),
+    "vox_stream_open": (C.c_int32, [_P, C.POINTER(C.c_int32)]),
+    "vox_stream_push_pcm": (C.c_int32, [_P, C.c_int32, _P, C.c_size_t]),
+    "vox_stream_finish": (C.c_int32, [_P, C.c_int32]),
+    "vox_stream_tick": (C.c_int32, [_P, _P]),
+    "vox_stream_poll_ids": (C.c_int32, [_P, C.c_int32, _P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]),
+    "vox_stream_audio_embeds": (C.c_int32, [_P, C.c_int32, _P, C.c_size_t, C.POINTER(C.c_int32)]),
+    "vox_stream_close": (C.c_int32, [_P, C.c_int32]),
+    "vox_stream_pool_free": (None, [_P]),
     "vox_tokenizer_from_file": (C.c_int32, [C.c_char_p, C.POINTER(_P)]),
     "vox_tokenizer_from_json": (C.c_int32, [C.c_char_p, C.c_size_t, C.POINTER(_P)]),
     "vox_tokenizer_decode": (C.c_int32, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -649,6 +658,66 @@ class Q4VoxtralModel:
         if getattr(self, "_m", None):
             lib().vox_model_free(self._m)
             self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _StreamStats(C.Structure):
+    _fields_ = [("gpu_ms", C.c_float), ("live_sessions", C.c_int32), ("mel_frames", C.c_int32), ("encoder_rows", C.c_int32),
+                ("prefills", C.c_int32), ("decode_steps", C.c_int32), ("decode_rows", C.c_int32)]
+
+
+class StreamingPool:
+    """Live streaming sessions on one GPU worker (vox_stream_*).  `model` stays owned by the caller
+    and must outlive the pool."""
+
+    def __init__(self, model: "Q4VoxtralModel", max_sessions: int = 8, max_seconds: float = 30.0):
+        self._model = model
+        self._p = _P()
+        _check(lib().vox_stream_pool_create(model._m, max_sessions, max_seconds, C.byref(self._p)))
+        self.dec_dim = model.info["dec_dim"]
+
+    def open(self) -> int:
+        v = C.c_int32()
+        _check(lib().vox_stream_open(self._p, C.byref(v)))
+        return v.value
+
+    def push(self, session: int, samples):
+        s = _f32(samples).reshape(-1)
+        _check(lib().vox_stream_push_pcm(self._p, session, _ptr(s), s.size))
+
+    def finish(self, session: int):
+        _check(lib().vox_stream_finish(self._p, session))
+
+    def tick(self) -> dict:
+        st = _StreamStats()
+        _check(lib().vox_stream_tick(self._p, C.byref(st)))
+        return {f[0]: getattr(st, f[0]) for f in _StreamStats._fields_}
+
+    def poll(self, session: int, cap: int = 4096):
+        ids = np.empty(cap, np.int32)
+        n, done = C.c_size_t(), C.c_int32()
+        _check(lib().vox_stream_poll_ids(self._p, session, _ptr(ids), cap, C.byref(n), C.byref(done)))
+        return ids[:n.value].tolist(), bool(done.value)
+
+    def audio_embeds(self, session: int) -> np.ndarray:
+        n = C.c_int32()
+        _check(lib().vox_stream_audio_embeds(self._p, session, None, 0, C.byref(n)))
+        out = np.empty((n.value, self.dec_dim), np.float32)
+        _check(lib().vox_stream_audio_embeds(self._p, session, _ptr(out), out.size, C.byref(n)))
+        return out
+
+    def close_session(self, session: int):
+        _check(lib().vox_stream_close(self._p, session))
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().vox_stream_pool_free(self._p)
+            self._p = None
 
     def __del__(self):
         try:

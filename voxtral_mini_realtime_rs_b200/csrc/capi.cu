@@ -14,6 +14,7 @@
 #include "gguf.h"
 #include "kernels.h"
 #include "model.h"
+#include "stream.h"
 #include "tokenizer.h"
 
 namespace vox {
@@ -66,6 +67,7 @@ struct vox_q4 {
 struct vox_model { Model *m; };
 struct vox_session { Session *s; };
 struct vox_tokenizer { Tokenizer *t; };
+struct vox_stream_pool { StreamPool *p; };
 
 static void require_device(int device) {
     int n = 0;
@@ -649,7 +651,7 @@ int32_t vox_generate_step_with_cache(vox_session *sh, const int32_t *ids, int32_
     launch_embed(s->m->tok_emb, s->d_ids, nullptr, 0, b, m, nullptr, s->x_dec, s->fused_decode(b * m) ? s->ssq_x : nullptr, s->st);
     const bool pending = s->decoder_forward(b, m);
     s->lm_head_rows(b * m, pending, s->logits_all);
-    launch_advance(s->d_pos, m, nullptr, 0, s->st);
+    launch_advance(s->d_pos, m, nullptr, 0, b, s->st);
     CUDA_OK(cudaMemcpyAsync(logits, s->logits_all, sizeof(float) * n, cudaMemcpyDeviceToHost, s->st));
     CUDA_OK(cudaStreamSynchronize(s->st));
     s->cache_len += m;
@@ -687,7 +689,7 @@ int32_t vox_forward_streaming(vox_session *sh, const float *mel, int32_t b, int3
         launch_embed(s->m->tok_emb, s->d_ids, s->audio, S4, b, m, s->d_pos, s->x_dec, s->fused_decode(b * m) ? s->ssq_x : nullptr, s->st);
         const bool pending = s->decoder_forward(b, m);
         s->lm_head_rows(b * m, pending, s->logits_all);
-        launch_advance(s->d_pos, m, nullptr, 0, s->st);
+        launch_advance(s->d_pos, m, nullptr, 0, b, s->st);
         for (int bb = 0; bb < b; ++bb)
             CUDA_OK(cudaMemcpyAsync(logits + ((size_t)bb * S4 + p0) * c.vocab, s->logits_all + (size_t)bb * m * c.vocab,
                                     sizeof(float) * (size_t)m * c.vocab, cudaMemcpyDeviceToHost, s->st));
@@ -826,6 +828,40 @@ int32_t vox_session_debug_read(vox_session *sh, const char *what, float *out, si
             for (size_t i = 0; i < cnt; ++i) out[i] = (float)((double)(t[i] - t[0]) / ((double)khz * 1e-3));
         }
         return VOX_OK;
+    } else if (w == "mega_trace_w") {
+        // [16 warps][6 groups][8] SM cycles relative to the earliest stamp (CTA 0, lm_head phase)
+        VOX_CHECK(s->mega_trace_w != nullptr, VOX_ENOTFOUND, "warp trace not enabled (VOX_MEGA_TRACE_ALL=1 at session creation)");
+        const size_t cnt = 16 * 6 * 8;
+        if (n_floats) *n_floats = cnt;
+        if (out) {
+            VOX_CHECK(cap >= cnt, VOX_ECAPACITY, "debug_read capacity %zu < %zu", cap, cnt);
+            CUDA_OK(cudaStreamSynchronize(s->st));
+            std::vector<unsigned long long> t(cnt);
+            CUDA_OK(cudaMemcpy(t.data(), s->mega_trace_w, sizeof(unsigned long long) * cnt, cudaMemcpyDeviceToHost));
+            unsigned long long t0 = ~0ull;
+            for (auto v : t) if (v != 0 && v < t0) t0 = v;
+            for (size_t i = 0; i < cnt; ++i) out[i] = t[i] ? (float)(t[i] - t0) : -1.0f;
+        }
+        return VOX_OK;
+    } else if (w == "mega_trace_all") {
+        // [grid][n_ops][4] microseconds relative to each CTA's exit from the first grid barrier (VOX_MEGA_TRACE_ALL=1)
+        VOX_CHECK(s->mega_trace_all != nullptr, VOX_ENOTFOUND, "all-CTA trace not enabled (VOX_MEGA_TRACE_ALL=1 at session creation)");
+        const size_t per = (size_t)s->mega_n_ops * 4, cnt = per * s->mega_grid;
+        if (n_floats) *n_floats = cnt;
+        if (out) {
+            VOX_CHECK(cap >= cnt, VOX_ECAPACITY, "debug_read capacity %zu < %zu", cap, cnt);
+            CUDA_OK(cudaStreamSynchronize(s->st));
+            std::vector<unsigned long long> t(cnt);
+            if (cnt) CUDA_OK(cudaMemcpy(t.data(), s->mega_trace_all, sizeof(unsigned long long) * cnt, cudaMemcpyDeviceToHost));
+            int khz = 0;
+            CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, s->m->device));
+            for (int ctai = 0; ctai < s->mega_grid; ++ctai) {
+                const unsigned long long t0 = t[(size_t)ctai * per + 2];
+                for (size_t i = 0; i < per; ++i)
+                    out[(size_t)ctai * per + i] = (float)((double)((long long)(t[(size_t)ctai * per + i] - t0)) / ((double)khz * 1e-3));
+            }
+        }
+        return VOX_OK;
     } else if (w == "enc_out") { src = s->h_enc; n = rows * c.enc_dim; }
     else if (w == "audio_embeds") { src = s->audio; n = (size_t)s->cur_B * s->cur_S4 * c.dec_dim; }
     else if (w == "mel") { src = s->mel; n = 0; /* size unknown here */ }
@@ -858,6 +894,76 @@ void vox_session_free(vox_session *s) {
     cudaSetDevice(s->s->m->device);
     delete s->s;
     delete s;
+}
+
+// ---------------------------------------------------------------- streaming sessions
+int32_t vox_stream_pool_create(vox_model *m, int32_t max_sessions, float max_seconds, vox_stream_pool **out) {
+    VOX_API_BEGIN
+    REQUIRE(m); REQUIRE(out);
+    CUDA_OK(cudaSetDevice(m->m->device));
+    *out = new vox_stream_pool{StreamPool::create(m->m, max_sessions, max_seconds)};
+    VOX_API_END
+}
+int32_t vox_stream_open(vox_stream_pool *p, int32_t *session) {
+    VOX_API_BEGIN
+    REQUIRE(p); REQUIRE(session);
+    *session = p->p->open();
+    VOX_API_END
+}
+int32_t vox_stream_push_pcm(vox_stream_pool *p, int32_t session, const float *samples, size_t n) {
+    VOX_API_BEGIN
+    REQUIRE(p);
+    if (n) REQUIRE(samples);
+    p->p->push(session, samples, n);
+    VOX_API_END
+}
+int32_t vox_stream_finish(vox_stream_pool *p, int32_t session) {
+    VOX_API_BEGIN
+    REQUIRE(p);
+    p->p->finish(session);
+    VOX_API_END
+}
+int32_t vox_stream_tick(vox_stream_pool *p, vox_stream_stats *stats) {
+    VOX_API_BEGIN
+    REQUIRE(p);
+    p->p->tick(stats);
+    VOX_API_END
+}
+int32_t vox_stream_poll_ids(vox_stream_pool *p, int32_t session, int32_t *ids, size_t cap, size_t *n, int32_t *done) {
+    VOX_API_BEGIN
+    REQUIRE(p); REQUIRE(n);
+    if (cap) REQUIRE(ids);
+    bool d = false;
+    *n = p->p->poll(session, ids, cap, &d);
+    if (done) *done = d ? 1 : 0;
+    VOX_API_END
+}
+int32_t vox_stream_audio_embeds(vox_stream_pool *p, int32_t session, float *out, size_t cap, int32_t *n) {
+    VOX_API_BEGIN
+    REQUIRE(p); REQUIRE(n);
+    int cnt = 0;
+    const float *src = p->p->audio_embeds(session, &cnt);
+    *n = cnt;
+    if (out) {
+        const size_t need = (size_t)cnt * p->p->m->info.dec_dim;
+        VOX_CHECK(cap >= need, VOX_ECAPACITY, "audio_embeds capacity %zu < %zu", cap, need);
+        CUDA_OK(cudaSetDevice(p->p->m->device));
+        CUDA_OK(cudaStreamSynchronize(p->p->s->st));
+        if (need) CUDA_OK(cudaMemcpy(out, src, sizeof(float) * need, cudaMemcpyDeviceToHost));
+    }
+    VOX_API_END
+}
+int32_t vox_stream_close(vox_stream_pool *p, int32_t session) {
+    VOX_API_BEGIN
+    REQUIRE(p);
+    p->p->close(session);
+    VOX_API_END
+}
+void vox_stream_pool_free(vox_stream_pool *p) {
+    if (!p) return;
+    cudaSetDevice(p->p->m->device);
+    delete p->p;
+    delete p;
 }
 
 // ---------------------------------------------------------------- tokenizer

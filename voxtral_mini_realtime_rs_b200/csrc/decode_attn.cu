@@ -20,44 +20,44 @@ constexpr int DA_THREADS = DA_WARPS * 32;
 
 template <int G, int DPL>
 __global__ void __launch_bounds__(DA_THREADS)
-dec_attn_fused_kernel(const float *__restrict__ qkv, const int ld, const int H, const int Hkv, float *__restrict__ kc,
-                      float *__restrict__ vc, const int max_seq, const int *__restrict__ pos_ptr, const int window,
+dec_attn_fused_kernel(const float *__restrict__ qkv, const int ld, const int H, const int Hkv, const KvView kv, const int window,
                       const float scale, const float *__restrict__ cos_t, const float *__restrict__ sin_t,
                       float *__restrict__ out) {
     constexpr int HD = DPL * 32;
     __shared__ float qs[G][HD];
-    __shared__ float kv[2][HD];
+    __shared__ float kvs[2][HD];
     __shared__ float red_m[DA_WARPS][G], red_l[DA_WARPS][G];
     __shared__ float red_acc[DA_WARPS][G][HD];
     // let the next kernel (the wo matvec) start prefetching its weights while we run
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const int kvh = blockIdx.x, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pos = *pos_ptr;
-    if (pos >= max_seq) return;
+    const int pos = kv.pos[b];
+    if (pos >= kv.max_seq()) return;
     const float *row = qkv + (size_t)b * ld;  // M = 1: one row per stream
     // ---- load q (G heads), k, v of this group; RoPE q and k; append k, v at `pos`
     for (int i = threadIdx.x; i < G * HD; i += DA_THREADS) qs[i / HD][i % HD] = row[(kvh * G + i / HD) * HD + i % HD];
     for (int i = threadIdx.x; i < HD; i += DA_THREADS) {
-        kv[0][i] = row[H * HD + kvh * HD + i];
-        kv[1][i] = row[(H + Hkv) * HD + kvh * HD + i];
+        kvs[0][i] = row[H * HD + kvh * HD + i];
+        kvs[1][i] = row[(H + Hkv) * HD + kvh * HD + i];
     }
     __syncthreads();
     const int half = HD / 2;
     for (int i = threadIdx.x; i < (G + 1) * half; i += DA_THREADS) {
         const int h = i / half, p = i - h * half;
-        float *v = (h < G) ? &qs[h][2 * p] : &kv[0][2 * p];
+        float *v = (h < G) ? &qs[h][2 * p] : &kvs[0][2 * p];
         const float c = cos_t[(size_t)pos * half + p], s = sin_t[(size_t)pos * half + p];
         const float xr = v[0], xi = v[1];
         v[0] = xr * c - xi * s;
         v[1] = xr * s + xi * c;
     }
     __syncthreads();
-    float *kbase = kc + ((size_t)b * Hkv + kvh) * max_seq * HD;
-    float *vbase = vc + ((size_t)b * Hkv + kvh) * max_seq * HD;
-    for (int i = threadIdx.x; i < HD; i += DA_THREADS) {
-        kbase[(size_t)pos * HD + i] = kv[0][i];
-        vbase[(size_t)pos * HD + i] = kv[1][i];
+    {
+        const size_t at = kv_index(kv, b, Hkv, kvh, pos, HD);
+        for (int i = threadIdx.x; i < HD; i += DA_THREADS) {
+            kv.k[at + i] = kvs[0][i];
+            kv.v[at + i] = kvs[1][i];
+        }
     }
     __syncthreads();  // the CTA's own global writes are visible to all its threads after the barrier
 
@@ -77,8 +77,9 @@ dec_attn_fused_kernel(const float *__restrict__ qkv, const int ld, const int H, 
     const int j_lo = pos - window > 0 ? pos - window : 0;
     for (int j = j_lo + warp; j <= pos; j += DA_WARPS) {
         float kk[DPL], vv[DPL];
-        const float *kr = kbase + (size_t)j * HD + lane * DPL;
-        const float *vr = vbase + (size_t)j * HD + lane * DPL;
+        const size_t at = kv_index(kv, b, Hkv, kvh, j, HD) + lane * DPL;
+        const float *kr = kv.k + at;
+        const float *vr = kv.v + at;
 #pragma unroll
         for (int i = 0; i < DPL; ++i) {
             kk[i] = kr[i];
@@ -136,13 +137,12 @@ dec_attn_fused_kernel(const float *__restrict__ qkv, const int ld, const int H, 
 }
 
 template <int G>
-void launch_g(int dpl, dim3 grid, cudaStream_t st, const float *qkv, int ld, int H, int Hkv, float *kc, float *vc,
-              int max_seq, const int *pos_ptr, int window, float scale, const float *cos_t, const float *sin_t,
-              float *out) {
+void launch_g(int dpl, dim3 grid, cudaStream_t st, const float *qkv, int ld, int H, int Hkv, const KvView &kv, int window,
+              float scale, const float *cos_t, const float *sin_t, float *out) {
     switch (dpl) {
-        case 1: dec_attn_fused_kernel<G, 1><<<grid, DA_THREADS, 0, st>>>(qkv, ld, H, Hkv, kc, vc, max_seq, pos_ptr, window, scale, cos_t, sin_t, out); break;
-        case 2: dec_attn_fused_kernel<G, 2><<<grid, DA_THREADS, 0, st>>>(qkv, ld, H, Hkv, kc, vc, max_seq, pos_ptr, window, scale, cos_t, sin_t, out); break;
-        case 4: dec_attn_fused_kernel<G, 4><<<grid, DA_THREADS, 0, st>>>(qkv, ld, H, Hkv, kc, vc, max_seq, pos_ptr, window, scale, cos_t, sin_t, out); break;
+        case 1: dec_attn_fused_kernel<G, 1><<<grid, DA_THREADS, 0, st>>>(qkv, ld, H, Hkv, kv, window, scale, cos_t, sin_t, out); break;
+        case 2: dec_attn_fused_kernel<G, 2><<<grid, DA_THREADS, 0, st>>>(qkv, ld, H, Hkv, kv, window, scale, cos_t, sin_t, out); break;
+        case 4: dec_attn_fused_kernel<G, 4><<<grid, DA_THREADS, 0, st>>>(qkv, ld, H, Hkv, kv, window, scale, cos_t, sin_t, out); break;
         default: fail(VOX_EINVAL, "dec_attn_fused: unsupported head_dim");
     }
 }
@@ -154,16 +154,15 @@ bool dec_attn_fused_supported(int H, int Hkv, int hd) {
     return (hd == 32 || hd == 64 || hd == 128) && (G == 1 || G == 2 || G == 4) && H % Hkv == 0;
 }
 
-void launch_dec_attn_fused(float *qkv, int B, int ld, int H, int Hkv, int hd, float *kc, float *vc, int max_seq,
-                           const int *pos_ptr, int window, float scale, const float *cos_t, const float *sin_t,
-                           float *out, cudaStream_t st) {
+void launch_dec_attn_fused(float *qkv, int B, int ld, int H, int Hkv, int hd, const KvView &kv, int window, float scale,
+                           const float *cos_t, const float *sin_t, float *out, cudaStream_t st) {
     VOX_CHECK(dec_attn_fused_supported(H, Hkv, hd), VOX_EINVAL, "dec_attn_fused: unsupported shape");
     const int G = H / Hkv, dpl = hd / 32;
     dim3 grid(Hkv, B);
     switch (G) {
-        case 1: launch_g<1>(dpl, grid, st, qkv, ld, H, Hkv, kc, vc, max_seq, pos_ptr, window, scale, cos_t, sin_t, out); break;
-        case 2: launch_g<2>(dpl, grid, st, qkv, ld, H, Hkv, kc, vc, max_seq, pos_ptr, window, scale, cos_t, sin_t, out); break;
-        default: launch_g<4>(dpl, grid, st, qkv, ld, H, Hkv, kc, vc, max_seq, pos_ptr, window, scale, cos_t, sin_t, out); break;
+        case 1: launch_g<1>(dpl, grid, st, qkv, ld, H, Hkv, kv, window, scale, cos_t, sin_t, out); break;
+        case 2: launch_g<2>(dpl, grid, st, qkv, ld, H, Hkv, kv, window, scale, cos_t, sin_t, out); break;
+        default: launch_g<4>(dpl, grid, st, qkv, ld, H, Hkv, kv, window, scale, cos_t, sin_t, out); break;
     }
     tc_count_launch("dec_attn_fused");
 }

@@ -42,7 +42,7 @@ struct MegaOp {
     float *ssq_out = nullptr;       // [n_tiles][B]
     int track_argmax = 0;
     // MG_ATTN
-    float *kc = nullptr, *vc = nullptr;  // this layer's caches [B][Hkv][max_seq][hd]
+    float *kc = nullptr, *vc = nullptr;  // this layer's KV page pools [n_pages][Hkv][KV_PAGE][hd] (kernels.h KvView)
     int layer = 0;
 };
 
@@ -53,7 +53,9 @@ struct MegaParams {
     float eps = 0.f;
     // attention
     float *qkv = nullptr;
-    int ld_qkv = 0, H = 0, Hkv = 0, hd = 0, max_seq = 0, window = 0;
+    int ld_qkv = 0, H = 0, Hkv = 0, hd = 0, max_seq = 0, window = 0;  // max_seq = max_pages * KV_PAGE
+    const int *page_table = nullptr;  // [B][max_pages] physical KV pages of each batch row
+    int max_pages = 0;
     float scale = 0.f;
     const float *cos_t = nullptr, *sin_t = nullptr;
     float *attn_out = nullptr;
@@ -68,13 +70,14 @@ struct MegaParams {
     int D = 0;
     const float *audio = nullptr;
     int audio_seq = 0;
+    const float *const *audio_rows = nullptr;  // optional [B]: the audio embedding of each row's current position (streaming)
     float *x_dec = nullptr, *ssq_x = nullptr;
     uint2 *emb_fbf = nullptr;         // fragments of the embedded row (x first layer's attn_norm) for layer 0
     float2 *emb_foff = nullptr;
     const float *emb_gamma = nullptr;
     uint2 *att_fbf = nullptr;         // fragments of the attention output (input of wo)
     float2 *att_foff = nullptr;
-    // device-side step state
+    // device-side step state; d_pos / d_outpos are PER ROW ([B]): sessions of different ages share a step
     int *d_pos = nullptr, *d_outpos = nullptr, *d_tok = nullptr, *d_out = nullptr;
     int out_ld = 0;
     // per-CTA argmax candidates [grid][8]
@@ -87,7 +90,13 @@ struct MegaParams {
     // optional phase trace of CTA 0: 6 SM-clock stamps per op (start, staged, body done, barrier passed,
     // first weights ready | KV walked, last weight stage consumed)
     unsigned long long *trace = nullptr;
-    // experiment switches (VOX_MEGA_FLAGS): 1 no evict-first hint, 2 no KV-cache L2 prefetch, 4 no norm-weight prefetch
+    // optional all-CTA trace [grid][n_ops][4]: op start, body done, barrier passed, first weights ready / KV walk
+    // start (SM clocks; the host aligns the CTAs on their exit from the first grid barrier)
+    unsigned long long *trace_all = nullptr;
+    // optional warp-level trace of CTA 0's first 6 tile groups of the lm_head phase: [16 warps][6 groups][8 stamps]
+    unsigned long long *trace_w = nullptr;
+    // experiment switches (VOX_MEGA_FLAGS): 1 no evict-first hint, 2 no KV-cache L2 prefetch, 4 no norm-weight prefetch,
+    // 8 fragments copied in one piece (no per-CTA rotation)
     int flags = 0;
 };
 

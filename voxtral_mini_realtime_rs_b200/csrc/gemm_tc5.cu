@@ -466,11 +466,8 @@ void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int 
     dim3 grid(w.N / G5_BM, a.TT, SK);
 #define G5_CASE(E)                                                                                              \
     case E: {                                                                                                   \
-        static bool set = false;                                                                                \
-        if (!set) {                                                                                             \
-            cudaFuncSetAttribute(gemm_tc5_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-            set = true;                                                                                         \
-        }                                                                                                       \
+        static SmemAttr attr;                                                                                   \
+        smem_attr_check(ensure_dyn_smem(gemm_tc5_kernel<E>, smem, attr), "gemm_tc5");                           \
         gemm_tc5_kernel<E><<<grid, G5_THREADS, smem, st>>>(a);                                                  \
         break;                                                                                                  \
     }

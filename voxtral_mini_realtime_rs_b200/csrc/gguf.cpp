@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <functional>
+#include <cstdint>
 #include <cstring>
 
 #include "common.h"
@@ -17,14 +18,19 @@ namespace vox {
 static const uint32_t kMagic = 0x46554747u;  // "GGUF" LE (reader.rs:13)
 static const uint64_t kAlign = 32;           // reader.rs:14
 
+// Product of the dims; saturates at UINT64_MAX on overflow (parse() rejects such tensors).
 uint64_t GgufTensorInfo::num_elements() const {
     uint64_t n = 1;
-    for (uint64_t d : dims) n *= d;
+    for (uint64_t d : dims) {
+        if (d != 0 && n > UINT64_MAX / d) return UINT64_MAX;
+        n *= d;
+    }
     return n;
 }
 
 uint64_t GgufTensorInfo::byte_size() const {  // GgmlDtype::byte_size reader.rs:38-49
     uint64_t n = num_elements();
+    if (n > UINT64_MAX / 4) return UINT64_MAX;
     switch (dtype) {
         case VOX_DTYPE_F32: return n * 4;
         case VOX_DTYPE_F16: return n * 2;
@@ -87,7 +93,8 @@ Gguf *Gguf::open_shards(const void *const *bufs, const size_t *lens, size_t n) {
 
 // ShardedCursor::read (reader.rs:268-290): copy across shard boundaries.
 void Gguf::read_at(uint64_t pos, void *dst, size_t n) const {
-    VOX_CHECK(pos + n <= total_len_, VOX_EIO, "GGUF read past end (offset %llu + %zu > %llu)",
+    // overflow-safe: `pos` may come straight from a (crafted) file
+    VOX_CHECK(n <= total_len_ && pos <= total_len_ - n, VOX_EIO, "GGUF read past end (offset %llu + %zu > %llu)",
               (unsigned long long)pos, n, (unsigned long long)total_len_);
     uint8_t *out = (uint8_t *)dst;
     while (n > 0) {
@@ -114,7 +121,7 @@ struct Cursor {
 void Gguf::parse() {
     uint64_t pos = 0;
     auto rd = [&](void *dst, size_t n, const char *what) {
-        if (pos + n > total_len_) fail(VOX_EIO, fmt("Failed to read %s", what));
+        if (n > total_len_ || pos > total_len_ - n) fail(VOX_EIO, fmt("Failed to read %s", what));
         read_at(pos, dst, n);
         pos += n;
     };
@@ -135,8 +142,9 @@ void Gguf::parse() {
     uint64_t kv_count = r_u64("metadata KV count");
 
     // skip_gguf_value (reader.rs:327-376); u32 values are additionally remembered.
-    std::function<void(uint32_t, const std::string *)> skip;
-    skip = [&](uint32_t t, const std::string *key) {
+    std::function<void(uint32_t, const std::string *, int)> skip;
+    skip = [&](uint32_t t, const std::string *key, int depth) {
+        VOX_CHECK(depth <= 16, VOX_EFORMAT, "GGUF metadata arrays nested deeper than 16");
         switch (t) {
             case 0: case 1: case 7: pos += 1; break;
             case 2: case 3: pos += 2; break;
@@ -150,7 +158,8 @@ void Gguf::parse() {
             case 9: {
                 uint32_t et = r_u32("array type");
                 uint64_t cnt = r_u64("array count");
-                for (uint64_t i = 0; i < cnt; ++i) skip(et, nullptr);
+                VOX_CHECK(cnt <= total_len_, VOX_EIO, "Failed to skip metadata value (array count %llu)", (unsigned long long)cnt);
+                for (uint64_t i = 0; i < cnt; ++i) skip(et, nullptr, depth + 1);
                 break;
             }
             case 10: case 11: case 12: pos += 8; break;
@@ -161,7 +170,7 @@ void Gguf::parse() {
     for (uint64_t i = 0; i < kv_count; ++i) {
         std::string key = r_str("metadata key");
         uint32_t vt = r_u32("metadata value type");
-        skip(vt, &key);
+        skip(vt, &key, 0);
     }
     for (uint64_t i = 0; i < tensor_count_; ++i) {
         GgufTensorInfo t;
@@ -176,6 +185,19 @@ void Gguf::parse() {
         tensors_[t.name] = t;
     }
     data_offset_ = (pos + kAlign - 1) / kAlign * kAlign;  // reader.rs:177-179
+    // every tensor's extent must lie inside the file (overflow-checked): the reference's reader errors out of
+    // read_exact here; we refuse at parse time so that no later read can run past a shard
+    VOX_CHECK(data_offset_ <= total_len_ || tensor_count_ == 0, VOX_EIO, "GGUF data section starts past the end of the file");
+    for (const auto &kv : tensors_) {
+        const GgufTensorInfo &t = kv.second;
+        const uint64_t nb = t.byte_size();
+        VOX_CHECK(t.num_elements() != UINT64_MAX && nb != UINT64_MAX, VOX_EFORMAT, "Tensor '%s': element count overflows", t.name.c_str());
+        if (t.dtype == VOX_DTYPE_Q4_0)
+            VOX_CHECK(t.num_elements() % 32 == 0, VOX_EFORMAT, "Tensor '%s': Q4_0 element count not a multiple of 32", t.name.c_str());
+        const uint64_t room = total_len_ - data_offset_;
+        VOX_CHECK(t.offset <= room && nb <= room - t.offset, VOX_EIO, "Tensor '%s' extends past the end of the file (offset %llu, %llu bytes)",
+                  t.name.c_str(), (unsigned long long)t.offset, (unsigned long long)nb);
+    }
 }
 
 const GgufTensorInfo *Gguf::find(const std::string &name) const {

@@ -12,6 +12,11 @@
 
 namespace vox {
 
+void smem_attr_check(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) fail(VOX_ECUDA, fmt("cudaFuncSetAttribute(%s, MaxDynamicSharedMemorySize): %s", what, cudaGetErrorString(e)));
+}
+
+
 static std::atomic<uint64_t> g_launches{0};
 uint64_t kernel_launch_count() { return g_launches.load(); }
 void add_graph_launches(int64_t n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
@@ -204,11 +209,8 @@ static void matvec_launch_t(const Q4Weight &w, const float *x, float *y, int ldy
     else kcb = (kcb / 32) * 32;
     const int n_chunks = (bpr + kcb - 1) / kcb;
     const size_t smem = (size_t)M * kcb * (XPAD + 1) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(q4_matvec_kernel<M, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
-    }
+    static SmemAttr attr;
+    smem_attr_check(ensure_dyn_smem(q4_matvec_kernel<M, EPI>, 100 * 1024, attr), "q4_matvec");
     const int n_rg = (w.N + MV_ROWS - 1) / MV_ROWS;
     int grid = n_rg;
     if (n_chunks == 1 && grid > 148 * 8) grid = 148 * 8;
@@ -264,6 +266,7 @@ struct GemmArgs {
     const float *bias;
     const float *res;
     int T_in, T_out, C_in;
+    int t_off;  // implicit im2col: output row t of the launch is conv output t + t_off (streaming: only the new frames)
 };
 
 template <int BMODE, int AMODE, int EPI>
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(GB_THREADS) gemm_kernel(const GemmArgs p) {
                 } else {
                     const int b = gm / p.T_out, t = gm - b * p.T_out;
                     const int tap = k0 / p.C_in, c0 = k0 - tap * p.C_in;
-                    const int tin = 2 * t - 1 + tap;
+                    const int tin = 2 * (t + p.t_off) - 1 + tap;
                     if (tin >= 0 && tin < p.T_in)
                         v = *reinterpret_cast<const float4 *>(p.a + ((size_t)b * p.T_in + tin) * p.C_in + c0 + kq * 4);
                 }
@@ -402,12 +405,14 @@ void launch_q4_gemm(const Q4Weight &w, const float *a, int M, float *y, int ldy,
 }
 
 void launch_conv2_gemm(const float *in, const float *w, const float *bias, float *out, int B, int T_in,
-                       int T_out, int C_in, int C_out, cudaStream_t st) {
+                       int T_out, int C_in, int C_out, cudaStream_t st, int t_off) {
     VOX_CHECK(C_in % 32 == 0, VOX_EINVAL, "conv2: C_in=%d not a multiple of 32", C_in);
+    VOX_CHECK(t_off == 0 || B == 1, VOX_EINVAL, "conv2: a frame offset needs B == 1");
+    if (B * T_out <= 0) return;
     GemmArgs p{};
     p.a = in; p.M = B * T_out; p.N = C_out; p.K = 3 * C_in; p.lda = 0;
     p.wf = w; p.y = out; p.ldy = C_out; p.bias = bias; p.res = nullptr;
-    p.T_in = T_in; p.T_out = T_out; p.C_in = C_in;
+    p.T_in = T_in; p.T_out = T_out; p.C_in = C_in; p.t_off = t_off;
     gemm_launch<1, 1>(p, EPI_GELU, st);
 }
 
@@ -603,12 +608,8 @@ void launch_enc_attention(const float *qkv, float *out, int B, int S, int H, int
     const size_t smem = (size_t)(EA_BQ * (hd + 1) + EA_BK * (hd + 1) + EA_BK * hd + EA_BQ * (EA_BK + 1)) * sizeof(float);
 #define ENC_ATTN_CASE(HD)                                                                                   \
     case HD: {                                                                                              \
-        static bool set = false;                                                                            \
-        if (!set) {                                                                                         \
-            cudaFuncSetAttribute(enc_attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                 (int)smem);                                                                \
-            set = true;                                                                                     \
-        }                                                                                                   \
+        static SmemAttr attr;                                                                               \
+        smem_attr_check(ensure_dyn_smem(enc_attention_kernel<HD>, smem, attr), "enc_attention");              \
         enc_attention_kernel<HD><<<grid, EA_THREADS, smem, st>>>(qkv, out, S, H, ld, q_off, k_off, v_off,   \
                                                                  window, scale);                            \
         break;                                                                                              \
@@ -628,12 +629,11 @@ void launch_enc_attention(const float *qkv, float *out, int B, int S, int H, int
 // cache without materialising the repeated K/V (model.rs:125-197).  Positions come from a device
 // counter so the same CUDA graph can be replayed for every step.
 // =====================================================================================
-__global__ void dec_rope_append_kernel(float *qkv, int M, int ld, int H, int Hkv, int hd, float *kc, float *vc,
-                                       int max_seq, const int *__restrict__ pos_ptr,
+__global__ void dec_rope_append_kernel(float *qkv, int M, int ld, int H, int Hkv, int hd, const KvView kv,
                                        const float *__restrict__ cos_t, const float *__restrict__ sin_t) {
     const int i = blockIdx.x, b = blockIdx.y;
-    const int pos = *pos_ptr + i;
-    if (pos >= max_seq) return;
+    const int pos = kv.pos[b] + i;
+    if (pos >= kv.max_seq()) return;
     const int half = hd >> 1;
     float *row = qkv + ((size_t)b * M + i) * ld;
     const float *cr = cos_t + (size_t)pos * half, *sr = sin_t + (size_t)pos * half;
@@ -649,34 +649,32 @@ __global__ void dec_rope_append_kernel(float *qkv, int M, int ld, int H, int Hkv
     for (int t = threadIdx.x; t < Hkv * half; t += blockDim.x) {
         const int h = t / half, p = t - h * half;
         const float xr = krow[h * hd + 2 * p], xi = krow[h * hd + 2 * p + 1];
-        float *dst = kc + (((size_t)b * Hkv + h) * max_seq + pos) * hd + 2 * p;
+        float *dst = kv.k + kv_index(kv, b, Hkv, h, pos, hd) + 2 * p;
         dst[0] = xr * cr[p] - xi * sr[p];
         dst[1] = xr * sr[p] + xi * cr[p];
     }
     for (int t = threadIdx.x; t < Hkv * hd; t += blockDim.x) {
         const int h = t / hd, d = t - h * hd;
-        vc[(((size_t)b * Hkv + h) * max_seq + pos) * hd + d] = vrow[t];
+        kv.v[kv_index(kv, b, Hkv, h, pos, hd) + d] = vrow[t];
     }
 }
 
-void launch_dec_rope_append(float *qkv, int B, int M, int ld, int H, int Hkv, int hd, float *kc, float *vc,
-                            int max_seq, const int *pos_ptr, const float *cos_t, const float *sin_t,
-                            cudaStream_t st) {
+void launch_dec_rope_append(float *qkv, int B, int M, int ld, int H, int Hkv, int hd, const KvView &kv,
+                            const float *cos_t, const float *sin_t, cudaStream_t st) {
     dim3 grid(M, B);
-    dec_rope_append_kernel<<<grid, 256, 0, st>>>(qkv, M, ld, H, Hkv, hd, kc, vc, max_seq, pos_ptr, cos_t, sin_t);
+    dec_rope_append_kernel<<<grid, 256, 0, st>>>(qkv, M, ld, H, Hkv, hd, kv, cos_t, sin_t);
     post_launch("dec_rope_append");
 }
 
 // grid (Hkv, M, B); block = 32 * (H/Hkv): one warp per query head of the group.
-__global__ void dec_attention_kernel(const float *__restrict__ qkv, int M, int ld, int H, int Hkv, int hd,
-                                     const float *__restrict__ kc, const float *__restrict__ vc, int max_seq,
-                                     const int *__restrict__ pos_ptr, int window, float scale,
-                                     float *__restrict__ out) {
+__global__ void dec_attention_kernel(const float *__restrict__ qkv, int M, int ld, int H, int Hkv, int hd, const KvView kv,
+                                     int window, float scale, float *__restrict__ out) {
     extern __shared__ float sm[];
     const int kvh = blockIdx.x, i = blockIdx.y, b = blockIdx.z;
     const int G = H / Hkv;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pos = *pos_ptr + i;
+    const int pos = kv.pos[b] + i;
+    const int max_seq = kv.max_seq();
     if (pos >= max_seq) return;
     float *qsm = sm + warp * hd;                        // [G][hd]
     float *sc = sm + G * hd + (size_t)warp * max_seq;   // [G][max_seq]
@@ -684,21 +682,19 @@ __global__ void dec_attention_kernel(const float *__restrict__ qkv, int M, int l
     const float *qrow = qkv + ((size_t)b * M + i) * ld + h * hd;
     for (int d = lane; d < hd; d += 32) qsm[d] = qrow[d];
     __syncwarp();
-    const float *kbase = kc + ((size_t)b * Hkv + kvh) * max_seq * hd;
-    const float *vbase = vc + ((size_t)b * Hkv + kvh) * max_seq * hd;
     const int j_lo = pos - window > 0 ? pos - window : 0;
     float mx = -INFINITY;
     for (int j = j_lo + lane; j <= pos; j += 32) {
-        const float4 *kr = reinterpret_cast<const float4 *>(kbase + (size_t)j * hd);
+        const float4 *kr = reinterpret_cast<const float4 *>(kv.k + kv_index(kv, b, Hkv, kvh, j, hd));
         const float4 *q4 = reinterpret_cast<const float4 *>(qsm);
         float acc = 0.0f;
         for (int d = 0; d < (hd >> 2); ++d) {
-            const float4 kv = kr[d];
+            const float4 kk = kr[d];
             const float4 qv = q4[d];
-            acc = fmaf(qv.x, kv.x, acc);
-            acc = fmaf(qv.y, kv.y, acc);
-            acc = fmaf(qv.z, kv.z, acc);
-            acc = fmaf(qv.w, kv.w, acc);
+            acc = fmaf(qv.x, kk.x, acc);
+            acc = fmaf(qv.y, kk.y, acc);
+            acc = fmaf(qv.z, kk.z, acc);
+            acc = fmaf(qv.w, kk.w, acc);
         }
         acc *= scale;
         sc[j] = acc;
@@ -717,25 +713,20 @@ __global__ void dec_attention_kernel(const float *__restrict__ qkv, int M, int l
     float *orow = out + ((size_t)b * M + i) * (H * hd) + h * hd;
     for (int d = lane; d < hd; d += 32) {
         float acc = 0.0f;
-        for (int j = j_lo; j <= pos; ++j) acc = fmaf(sc[j], vbase[(size_t)j * hd + d], acc);
+        for (int j = j_lo; j <= pos; ++j) acc = fmaf(sc[j], kv.v[kv_index(kv, b, Hkv, kvh, j, hd) + d], acc);
         orow[d] = acc * inv;
     }
 }
 
-void launch_dec_attention(const float *qkv, int B, int M, int ld, int H, int Hkv, int hd, const float *kc,
-                          const float *vc, int max_seq, const int *pos_ptr, int window, float scale,
-                          float *out, cudaStream_t st) {
+void launch_dec_attention(const float *qkv, int B, int M, int ld, int H, int Hkv, int hd, const KvView &kv, int window,
+                          float scale, float *out, cudaStream_t st) {
     const int G = H / Hkv;
     dim3 grid(Hkv, M, B);
-    const size_t smem = (size_t)G * (hd + max_seq) * sizeof(float);
-    VOX_CHECK(smem <= 200 * 1024, VOX_EINVAL, "dec_attention: max_seq %d too large for the v1 kernel", max_seq);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(dec_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
-    }
-    dec_attention_kernel<<<grid, 32 * G, smem, st>>>(qkv, M, ld, H, Hkv, hd, kc, vc, max_seq, pos_ptr, window,
-                                                     scale, out);
+    const size_t smem = (size_t)G * (hd + kv.max_seq()) * sizeof(float);
+    VOX_CHECK(smem <= 200 * 1024, VOX_EINVAL, "dec_attention: max_seq %d too large for the v1 kernel", kv.max_seq());
+    static SmemAttr attr;
+    if (smem > 48 * 1024) smem_attr_check(ensure_dyn_smem(dec_attention_kernel, smem, attr), "dec_attention");
+    dec_attention_kernel<<<grid, 32 * G, smem, st>>>(qkv, M, ld, H, Hkv, hd, kv, window, scale, out);
     post_launch("dec_attention");
 }
 
@@ -745,15 +736,17 @@ void launch_dec_attention(const float *qkv, int B, int M, int ld, int H, int Hkv
 __global__ void embed_kernel(const uint4 *__restrict__ qs, const __half *__restrict__ ds, int K,
                              const int *__restrict__ ids, const float *__restrict__ audio, int audio_seq, int M,
                              const int *__restrict__ pos_ptr, float *__restrict__ x, float *__restrict__ ssq_out,
-                             const int rows_total) {
+                             const int rows_total, const float *const *__restrict__ audio_rows) {
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");  // PDL: next kernel may prefetch weights
     const int i = blockIdx.x, b = blockIdx.y;
     const int r = b * M + i;
     const int id = ids[r];
     const int bpr = K >> 5;
     const float *arow = nullptr;
-    if (audio) {
-        const int pos = (pos_ptr ? *pos_ptr : 0) + i;
+    if (audio_rows) {
+        arow = audio_rows[b] ? audio_rows[b] + (size_t)i * K : nullptr;
+    } else if (audio) {
+        const int pos = (pos_ptr ? pos_ptr[b] : 0) + i;
         arow = audio + ((size_t)b * audio_seq + pos) * K;
     }
     for (int t = threadIdx.x; t < bpr * 16; t += blockDim.x) {
@@ -783,9 +776,9 @@ __global__ void embed_kernel(const uint4 *__restrict__ qs, const __half *__restr
 }
 
 void launch_embed(const Q4Weight &emb, const int *ids, const float *audio, int audio_seq, int B, int M,
-                  const int *pos_ptr, float *x, float *ssq_out, cudaStream_t st) {
+                  const int *pos_ptr, float *x, float *ssq_out, cudaStream_t st, const float *const *audio_rows) {
     dim3 grid(M, B);
-    embed_kernel<<<grid, 256, 0, st>>>(emb.qs, emb.d, emb.K, ids, audio, audio_seq, M, pos_ptr, x, ssq_out, B * M);
+    embed_kernel<<<grid, 256, 0, st>>>(emb.qs, emb.d, emb.K, ids, audio, audio_seq, M, pos_ptr, x, ssq_out, B * M, audio_rows);
     post_launch("embed");
 }
 
@@ -826,7 +819,7 @@ __global__ void argmax_kernel(const float *__restrict__ logits, int V, int *tok,
         }
         if (threadIdx.x == 0) {
             tok[b] = bi;
-            if (out_ids) out_ids[(size_t)b * out_ld + *out_pos_ptr] = bi;
+            if (out_ids) out_ids[(size_t)b * out_ld + out_pos_ptr[b]] = bi;
         }
     }
 }
@@ -887,7 +880,7 @@ __global__ void argmax_multi_kernel(const float *__restrict__ logits, int V, int
         if (threadIdx.x == 0) {
             if (bi == 0x7fffffff) bi = 0;
             tok[b] = bi;
-            if (out_ids) out_ids[(size_t)b * out_ld + *out_pos_ptr] = bi;
+            if (out_ids) out_ids[(size_t)b * out_ld + out_pos_ptr[b]] = bi;
         }
     }
 }
@@ -900,13 +893,16 @@ void launch_argmax_multi(const float *logits, int B, int V, int *tok, int *out_i
     post_launch("argmax_multi");
 }
 
-__global__ void advance_kernel(int *a, int da, int *b, int db) {
+__global__ void advance_kernel(int *a, int da, int *b, int db, int n) {
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    if (a) *a += da;
-    if (b) *b += db;
+    const int i = threadIdx.x;
+    if (i < n) {
+        if (a) a[i] += da;
+        if (b) b[i] += db;
+    }
 }
-void launch_advance(int *a, int da, int *b, int db, cudaStream_t st) {
-    advance_kernel<<<1, 1, 0, st>>>(a, da, b, db);
+void launch_advance(int *a, int da, int *b, int db, int n, cudaStream_t st) {
+    advance_kernel<<<1, 64, 0, st>>>(a, da, b, db, n);
     post_launch("advance");
 }
 
@@ -966,12 +962,12 @@ constexpr int MEL_FR = 8, MEL_THREADS = 256, MEL_NFFT = 400, MEL_HOP = 160, MEL_
 __global__ void __launch_bounds__(MEL_THREADS)
 mel_kernel(const float *__restrict__ samples, size_t n, size_t sample_stride, const float *__restrict__ window,
            const float *__restrict__ fb_vals, const int *__restrict__ fb_start, const int *__restrict__ fb_len,
-           int fb_stride, float *__restrict__ out, int frames, int layout) {
+           int fb_stride, float *__restrict__ out, int frames, int layout, int frame0) {
     __shared__ float ws[MEL_FR][MEL_NFFT];
     __shared__ float ct[MEL_NFFT], stt[MEL_NFFT];
     __shared__ float pw[MEL_FR][MEL_NFREQ + 3];
     const int b = blockIdx.y;
-    const int f0 = blockIdx.x * MEL_FR;
+    const int f0 = frame0 + blockIdx.x * MEL_FR;   // frames [frame0, frames) of the signal (streaming: only the new ones)
     const float *sig = samples + (size_t)b * sample_stride;
     const long long nn = (long long)n;
     for (int i = threadIdx.x; i < MEL_NFFT; i += MEL_THREADS) {
@@ -1031,11 +1027,11 @@ mel_kernel(const float *__restrict__ samples, size_t n, size_t sample_stride, co
 
 void launch_mel(const float *samples, int B, size_t n, size_t sample_stride, const float *window,
                 const float *fb_vals, const int *fb_start, const int *fb_len, int fb_stride, float *out,
-                int frames, int layout, cudaStream_t st) {
-    if (frames <= 0 || B <= 0) return;
-    dim3 grid((frames + MEL_FR - 1) / MEL_FR, B);
+                int frames, int layout, cudaStream_t st, int frame0) {
+    if (frames - frame0 <= 0 || B <= 0) return;
+    dim3 grid((frames - frame0 + MEL_FR - 1) / MEL_FR, B);
     mel_kernel<<<grid, MEL_THREADS, 0, st>>>(samples, n, sample_stride, window, fb_vals, fb_start, fb_len,
-                                             fb_stride, out, frames, layout);
+                                             fb_stride, out, frames, layout, frame0);
     post_launch("mel");
 }
 

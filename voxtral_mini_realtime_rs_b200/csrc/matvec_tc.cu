@@ -476,12 +476,8 @@ void tc_launch_t(TcArgs a, const TcWork *wk, cudaStream_t st) {
     const size_t act = misc + (size_t)Ps * 2 * M * sizeof(float2) + (size_t)Ps * 2 * 2 * 2 * M * 4 * sizeof(uint2);
     const size_t smem = act + 128 + (size_t)nbuf * slice_bytes + 64;
     VOX_CHECK(smem <= 200 * 1024, VOX_EINVAL, "q4_matvec_tc: shared memory %zu too large (K=%d, M=%d)", smem, a.K, M);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cuda_check_tc(cudaFuncSetAttribute(q4_matvec_tc_kernel<M, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024),
-                      "cudaFuncSetAttribute(q4_matvec_tc)");
-        attr_set = true;
-    }
+    static SmemAttr smem_attr;
+    cuda_check_tc(ensure_dyn_smem(q4_matvec_tc_kernel<M, EPI>, 208 * 1024, smem_attr), "cudaFuncSetAttribute(q4_matvec_tc)");
     a.S = S;
     a.Ps = Ps;
     a.TG = TG;

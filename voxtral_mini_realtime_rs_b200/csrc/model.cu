@@ -267,14 +267,23 @@ Model *Model::load(const Gguf &g, int device) {
             c.n_mels = (int)s[1];
             VOX_CHECK(c.n_mels == kMelBins, VOX_EINVAL, "n_mels=%d unsupported (mel front-end is 128-bin)", c.n_mels);
         }
-        c.enc_ffn = (int)L.info(E + ".transformer.layers.0.feed_forward.w1.weight").shape()[0];
-        {
-            std::vector<int64_t> s = L.info(kTokEmb).shape();
-            c.vocab = (int)s[0];
-            c.dec_dim = (int)s[1];
-        }
-        c.dec_ffn = (int)L.info("layers.0.feed_forward.w1.weight").shape()[0];
-        c.t_cond_dim = (int)L.info("layers.0.ada_rms_norm_t_cond.0.weight").shape()[0];
+        // shapes come from the file: check the rank before indexing and the range before dividing
+        auto dim2 = [&](const std::string &name, int axis) {
+            std::vector<int64_t> s = L.info(name).shape();
+            VOX_CHECK(s.size() == 2, VOX_EINVAL, "Tensor '%s' must be 2-D (has %zu dims)", name.c_str(), s.size());
+            VOX_CHECK(s[axis] >= 1 && s[axis] <= (1 << 24), VOX_EINVAL, "Tensor '%s' dim %d = %lld out of range", name.c_str(), axis,
+                      (long long)s[axis]);
+            return (int)s[axis];
+        };
+        c.enc_ffn = dim2(E + ".transformer.layers.0.feed_forward.w1.weight", 0);
+        c.vocab = dim2(kTokEmb, 0);
+        c.dec_dim = dim2(kTokEmb, 1);
+        c.dec_ffn = dim2("layers.0.feed_forward.w1.weight", 0);
+        c.t_cond_dim = dim2("layers.0.ada_rms_norm_t_cond.0.weight", 0);
+        for (int v : {c.enc_layers, c.enc_heads, c.enc_head_dim, c.dec_layers, c.dec_heads, c.dec_kv_heads, c.dec_head_dim,
+                      c.reshape_factor, c.enc_dim})
+            VOX_CHECK(v >= 1 && v <= (1 << 20), VOX_EINVAL, "model dimension %d out of range (voxtral.* metadata)", v);
+        VOX_CHECK(c.enc_window >= 0 && c.dec_window >= 0, VOX_EINVAL, "negative sliding window");
         VOX_CHECK(c.dec_heads % c.dec_kv_heads == 0, VOX_EINVAL, "dec_heads %% dec_kv_heads != 0");
         VOX_CHECK(c.enc_head_dim == 32 || c.enc_head_dim == 64 || c.enc_head_dim == 128, VOX_EINVAL,
                   "encoder head_dim %d unsupported", c.enc_head_dim);
@@ -411,10 +420,16 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
         s->audio = s->arena.alloc_n<float>(rows4 * c.dec_dim);
         // decoder
         const int kv_cap = std::max(s->S4_max, s->M_max) + s->M_max;  // room for the incremental API
-        s->out_ld = kv_cap;
-        const size_t kv_elems = (size_t)c.dec_layers * B * c.dec_kv_heads * kv_cap * c.dec_head_dim;
+        s->kv_max_pages = (kv_cap + KV_PAGE - 1) / KV_PAGE;
+        s->kv_n_pages = max_batch * s->kv_max_pages;
+        s->out_ld = s->kv_max_pages * KV_PAGE;
+        const size_t kv_elems = (size_t)c.dec_layers * s->kv_n_pages * c.dec_kv_heads * KV_PAGE * c.dec_head_dim;
         s->kc = s->arena.alloc_n<float>(kv_elems);
         s->vc = s->arena.alloc_n<float>(kv_elems);
+        s->page_table_host.resize((size_t)max_batch * s->kv_max_pages);
+        for (int b = 0; b < max_batch; ++b)
+            for (int pg = 0; pg < s->kv_max_pages; ++pg) s->page_table_host[(size_t)b * s->kv_max_pages + pg] = b * s->kv_max_pages + pg;
+        s->d_page_table = s->arena.upload(s->page_table_host.data(), s->page_table_host.size());
         const size_t drows = B * s->M_max;
         const int qkvd = (c.dec_heads + 2 * c.dec_kv_heads) * c.dec_head_dim;
         s->x_dec = s->arena.alloc_n<float>(drows * c.dec_dim);
@@ -428,8 +443,8 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
         s->ffn_gamma_ada = s->arena.alloc_n<float>((size_t)c.dec_layers * c.dec_dim);
         s->t_embed = s->arena.alloc_n<float>(c.dec_dim);
         s->ada_tmp = s->arena.alloc_n<float>(c.t_cond_dim);
-        s->d_pos = s->arena.alloc_n<int>(1);
-        s->d_outpos = s->arena.alloc_n<int>(1);
+        s->d_pos = s->arena.alloc_n<int>(B);      // per row (kernels.h KvView::pos)
+        s->d_outpos = s->arena.alloc_n<int>(B);
         s->d_tok = s->arena.alloc_n<int>(B);
         s->d_ids = s->arena.alloc_n<int>(drows);
         s->d_out = s->arena.alloc_n<int>(B * s->out_ld);
@@ -512,9 +527,18 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
             }
             s->mega_trace = s->arena.alloc_n<unsigned long long>((size_t)s->mega_ops_cap * 6);
             CUDA_OK(cudaMemset(s->mega_trace, 0, sizeof(unsigned long long) * s->mega_ops_cap * 6));
+            if (const char *ta = getenv("VOX_MEGA_TRACE_ALL")) {
+                if (ta[0] == '1') {
+                    const size_t n = (size_t)s->mega_grid * s->mega_ops_cap * 4;
+                    s->mega_trace_all = s->arena.alloc_n<unsigned long long>(n);
+                    CUDA_OK(cudaMemset(s->mega_trace_all, 0, sizeof(unsigned long long) * n));
+                    s->mega_trace_w = s->arena.alloc_n<unsigned long long>(16 * 6 * 8);
+                    CUDA_OK(cudaMemset(s->mega_trace_w, 0, sizeof(unsigned long long) * 16 * 6 * 8));
+                }
+            }
         }
-        CUDA_OK(cudaMemset(s->d_pos, 0, sizeof(int)));
-        CUDA_OK(cudaMemset(s->d_outpos, 0, sizeof(int)));
+        CUDA_OK(cudaMemset(s->d_pos, 0, sizeof(int) * B));
+        CUDA_OK(cudaMemset(s->d_outpos, 0, sizeof(int) * B));
         s->set_delay(6.0f);  // CLI default --delay 6 (transcribe.rs:49-51)
     } catch (...) {
         delete s;
@@ -639,12 +663,21 @@ TcWork Session::tc_work(bool norm_in, bool ssq_out_) const {
     return w;
 }
 
+KvView Session::kv_view(int layer) const {
+    KvView v;
+    v.k = kc + (size_t)layer * kv_layer_stride();
+    v.v = vc + (size_t)layer * kv_layer_stride();
+    v.page_table = d_page_table;
+    v.max_pages = kv_max_pages;
+    v.pos = d_pos;
+    return v;
+}
+
 bool Session::decoder_forward(int B, int M) {
     const vox_model_info &c = m->info;
     const int D = c.dec_dim, H = c.dec_heads, Hkv = c.dec_kv_heads, hd = c.dec_head_dim;
     const int qkvd = (H + 2 * Hkv) * hd, rows = B * M;
     const float scale = powf((float)hd, -0.5f);
-    const size_t layer_stride = (size_t)max_batch * Hkv * out_ld * hd;
     // decode-sized problems: RMSNorm fused into the consuming matvec, RoPE + KV append fused into the
     // attention kernel => 5 launches per layer instead of 8
     const bool fused = fused_decode(rows);
@@ -652,7 +685,7 @@ bool Session::decoder_forward(int B, int M) {
     const bool fattn = fused && M == 1 && dec_attn_fused_supported(H, Hkv, hd);
     for (int j = 0; j < c.dec_layers; ++j) {
         const DecLayerW &l = m->dec[j];
-        float *kcl = kc + (size_t)j * layer_stride, *vcl = vc + (size_t)j * layer_stride;
+        const KvView kvl = kv_view(j);
         if (fused) {
             launch_q4_matvec_tc_ex(l.wqkv, x_dec, rows, qkv_dec, qkvd, nullptr, nullptr, EPI_NONE, l.attn_norm, nullptr,
                                    m->norm_eps, &wk_norm, st);
@@ -660,11 +693,10 @@ bool Session::decoder_forward(int B, int M) {
             linear_n(l.wqkv, x_dec, rows, qkv_dec, qkvd, nullptr, nullptr, EPI_NONE, l.attn_norm, nullptr, h_dec);
         }
         if (fattn) {
-            launch_dec_attn_fused(qkv_dec, B, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, c.dec_window, scale, m->dec_cos,
-                                  m->dec_sin, attn_dec, st);
+            launch_dec_attn_fused(qkv_dec, B, qkvd, H, Hkv, hd, kvl, c.dec_window, scale, m->dec_cos, m->dec_sin, attn_dec, st);
         } else {
-            launch_dec_rope_append(qkv_dec, B, M, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, m->dec_cos, m->dec_sin, st);
-            launch_dec_attention(qkv_dec, B, M, qkvd, H, Hkv, hd, kcl, vcl, out_ld, d_pos, c.dec_window, scale, attn_dec, st);
+            launch_dec_rope_append(qkv_dec, B, M, qkvd, H, Hkv, hd, kvl, m->dec_cos, m->dec_sin, st);
+            launch_dec_attention(qkv_dec, B, M, qkvd, H, Hkv, hd, kvl, c.dec_window, scale, attn_dec, st);
         }
         if (fused)
             launch_q4_matvec_tc_ex(l.wo, attn_dec, rows, x_dec, D, nullptr, x_dec, EPI_RESIDUAL, nullptr, nullptr, 0.f, &wk_res, st);
@@ -714,7 +746,7 @@ bool Session::mega_prepare(int B) {
     auto pairs = [](int K) { return (K / 32 + 1) / 2; };
     const int max_pairs = std::max(std::max(pairs(D), pairs(H * hd)), pairs(c.dec_ffn));
     mega_plan = decode_mega_plan(B, max_pairs, H, Hkv, hd);
-    const size_t layer_stride = (size_t)max_batch * Hkv * out_ld * hd;
+    const size_t layer_stride = kv_layer_stride();
     const int parts = (D + 15) / 16;
     std::vector<MegaOp> ops;
     bool ok = true;
@@ -822,6 +854,8 @@ void Session::decode_step(int B, bool add_audio) {
         p.Hkv = c.dec_kv_heads;
         p.hd = c.dec_head_dim;
         p.max_seq = out_ld;
+        p.page_table = d_page_table;
+        p.max_pages = kv_max_pages;
         p.window = c.dec_window;
         p.scale = powf((float)c.dec_head_dim, -0.5f);
         p.cos_t = m->dec_cos;
@@ -840,6 +874,7 @@ void Session::decode_step(int B, bool add_audio) {
         p.emb_d = m->tok_emb.d;
         p.D = c.dec_dim;
         p.audio = add_audio ? audio : nullptr;
+        p.audio_rows = add_audio ? audio_rows_dev : nullptr;
         p.audio_seq = cur_S4;
         p.x_dec = x_dec;
         p.ssq_x = ssq_x;
@@ -851,7 +886,7 @@ void Session::decode_step(int B, bool add_audio) {
         p.d_pos = d_pos;
         p.d_outpos = d_outpos;
         p.d_tok = d_tok;
-        p.d_out = d_out;
+        p.d_out = stream_mode ? nullptr : d_out;
         p.out_ld = out_ld;
         p.am_vals = mega_am_vals;
         p.am_idx = mega_am_idx;
@@ -859,6 +894,8 @@ void Session::decode_step(int B, bool add_audio) {
         p.nstage = mega_plan.nstage;
         p.scratch_bytes = mega_plan.scratch_bytes;
         p.trace = mega_trace;
+        p.trace_all = mega_trace_all;
+        p.trace_w = mega_trace_w;
         {
             static const int env_flags = getenv("VOX_MEGA_FLAGS") ? atoi(getenv("VOX_MEGA_FLAGS")) : 0;
             p.flags = env_flags;
@@ -866,18 +903,20 @@ void Session::decode_step(int B, bool add_audio) {
         launch_decode_mega(p, mega_plan, mega_grid, st);
         return;
     }
-    launch_embed(m->tok_emb, d_tok, add_audio ? audio : nullptr, cur_S4, B, 1, d_pos, x_dec, fused_decode(B) ? ssq_x : nullptr, st);
+    launch_embed(m->tok_emb, d_tok, add_audio ? audio : nullptr, cur_S4, B, 1, d_pos, x_dec, fused_decode(B) ? ssq_x : nullptr, st,
+                 add_audio ? audio_rows_dev : nullptr);
     const bool pending = decoder_forward(B, 1);
     lm_head_rows(B, pending, logits);
-    launch_argmax_multi(logits, B, c.vocab, d_tok, d_out, out_ld, d_outpos, am_vals, am_idx, am_cnt, st);
-    launch_advance(d_pos, 1, d_outpos, 1, st);
+    launch_argmax_multi(logits, B, c.vocab, d_tok, stream_mode ? nullptr : d_out, out_ld, d_outpos, am_vals, am_idx, am_cnt, st);
+    launch_advance(d_pos, 1, d_outpos, 1, B, st);
 }
 
 // Prefill of M positions for B streams (model.rs:894-923 with M = 38; also the incremental vox_prefill).
 void Session::prefill(int B, int M, const int *ids_host, bool add_audio) {
     const vox_model_info &c = m->info;
     CUDA_OK(cudaMemcpyAsync(d_ids, ids_host, sizeof(int) * (size_t)B * M, cudaMemcpyHostToDevice, st));
-    launch_embed(m->tok_emb, d_ids, add_audio ? audio : nullptr, cur_S4, B, M, d_pos, x_dec, fused_decode(B * M) ? ssq_x : nullptr, st);
+    launch_embed(m->tok_emb, d_ids, add_audio ? (audio_base ? audio_base : audio) : nullptr, audio_base ? S4_max : cur_S4, B, M, d_pos, x_dec,
+                 fused_decode(B * M) ? ssq_x : nullptr, st);
     const bool pending = decoder_forward(B, M);
     if (pending) {   // decode-sized prefill (B*M <= 8): final norm still pending in x_dec
         launch_rmsnorm(x_dec, m->dec_norm, nullptr, h_dec, B * M, c.dec_dim, m->norm_eps, st);
@@ -885,13 +924,13 @@ void Session::prefill(int B, int M, const int *ids_host, bool add_audio) {
     // lm_head on the last row only (the reference computes all M rows and keeps one)
     launch_gather_last(h_dec, last_h, B, M, c.dec_dim, st);
     linear(m->tok_emb, last_h, B, logits, c.vocab, nullptr, nullptr, EPI_NONE);
-    launch_argmax(logits, B, c.vocab, d_tok, d_out, out_ld, d_outpos, st);
-    launch_advance(d_pos, M, d_outpos, 1, st);
+    launch_argmax(logits, B, c.vocab, d_tok, stream_mode ? nullptr : d_out, out_ld, d_outpos, st);
+    launch_advance(d_pos, M, d_outpos, 1, B, st);
 }
 
 void Session::reset() {
-    CUDA_OK(cudaMemsetAsync(d_pos, 0, sizeof(int), st));
-    CUDA_OK(cudaMemsetAsync(d_outpos, 0, sizeof(int), st));
+    CUDA_OK(cudaMemsetAsync(d_pos, 0, sizeof(int) * max_batch, st));
+    CUDA_OK(cudaMemsetAsync(d_outpos, 0, sizeof(int) * max_batch, st));
     cache_len = 0;
     // the persistent kernel's attention-chunk flags carry epoch * 64 + layer + 1 (int): re-base the device
     // epoch long before that can overflow (2^24 steps ~ 10 hours of continuous decoding)

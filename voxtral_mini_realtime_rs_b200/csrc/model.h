@@ -96,7 +96,14 @@ struct Session {
     float *packed = nullptr, *adapter_h = nullptr, *audio = nullptr;
     int cur_B = 0, cur_S = 0, cur_S4 = 0;
     // decoder
-    float *kc = nullptr, *vc = nullptr;  // [L][B][Hkv][S4_max][hd]
+    // decoder KV cache: page pools [L][n_pages][Hkv][KV_PAGE][hd] + per-row page tables (kernels.h KvView).  Whole-
+    // utterance batches use the identity mapping (row b owns pages b*max_pages..); streaming sessions allocate pages
+    float *kc = nullptr, *vc = nullptr;
+    int kv_max_pages = 0, kv_n_pages = 0;
+    int *d_page_table = nullptr;          // [max_batch][kv_max_pages]
+    std::vector<int> page_table_host;
+    size_t kv_layer_stride() const { return (size_t)kv_n_pages * m->info.dec_kv_heads * KV_PAGE * m->info.dec_head_dim; }
+    KvView kv_view(int layer) const;
     float *x_dec = nullptr, *h_dec = nullptr, *qkv_dec = nullptr, *attn_dec = nullptr, *act_dec = nullptr;
     float *last_h = nullptr, *logits = nullptr;
     float *logits_all = nullptr;
@@ -106,7 +113,12 @@ struct Session {
     bool delay_set = false;
     int *d_pos = nullptr, *d_outpos = nullptr, *d_tok = nullptr, *d_ids = nullptr, *d_out = nullptr;
     int out_ld = 0;
-    int cache_len = 0;  // host mirror of *d_pos for the incremental API
+    int cache_len = 0;  // host mirror of d_pos[] (all rows equal) for the incremental API
+    // streaming pool (stream.cu): rows of a step belong to sessions of different ages -- no d_out history, audio
+    // embeddings through a per-row pointer table (decode) or a per-launch base pointer (single-session prefill)
+    bool stream_mode = false;
+    const float *const *audio_rows_dev = nullptr;
+    const float *audio_base = nullptr;
     cudaGraphExec_t step_graph = nullptr;
     int step_graph_B = 0, step_graph_S4 = 0;
     uint64_t step_graph_nodes = 0;
@@ -140,6 +152,8 @@ struct Session {
     uint2 *mega_xf_bf = nullptr, *mega_af_bf = nullptr, *mega_cf_bf = nullptr;
     float2 *mega_xf_off = nullptr, *mega_af_off = nullptr, *mega_cf_off = nullptr;
     size_t mega_xf_blocks = 0, mega_af_blocks = 0, mega_cf_blocks = 0;
+    unsigned long long *mega_trace_w = nullptr;    // [16][6][8] (debug "mega_trace_w", VOX_MEGA_TRACE_ALL=1)
+    unsigned long long *mega_trace_all = nullptr;  // [grid][mega_ops_cap][4] (debug "mega_trace_all", VOX_MEGA_TRACE_ALL=1)
     unsigned long long *mega_trace = nullptr;  // [mega_ops_cap][6] SM-clock stamps of CTA 0 (debug "mega_trace")
     bool mega_prepare(int B);
     bool fused_decode(int rows) const;

@@ -5,6 +5,7 @@
 #include "tokenizer.h"
 
 #include <cstdlib>
+#include <cctype>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -89,7 +90,14 @@ struct JParser {
         ++p;
         return o;
     }
+    int depth = 0;
+    struct Depth {   // recursion guard: a crafted "[[[[..." must be an error, not a stack overflow
+        JParser &ps;
+        explicit Depth(JParser &q) : ps(q) { if (++ps.depth > 64) ps.err("nesting deeper than 64"); }
+        ~Depth() { --ps.depth; }
+    };
     JVal val() {
+        Depth guard(*this);
         ws();
         if (p >= e) err("unexpected end");
         JVal v;
@@ -128,11 +136,20 @@ struct JParser {
         else if (c == 'f' && e - p >= 5 && !strncmp(p, "false", 5)) { v.t = JVal::Bool; v.b = false; p += 5; }
         else if (c == 'n' && e - p >= 4 && !strncmp(p, "null", 4)) { v.t = JVal::Null; p += 4; }
         else {
+            // the buffer is length-delimited, not NUL-terminated: copy the numeric token into a bounded buffer
+            // before strtod so that it cannot read past `e`
+            char tmp[64];
+            size_t n = 0;
+            while (p + n < e && n + 1 < sizeof(tmp) && (isdigit((unsigned char)p[n]) || p[n] == '-' || p[n] == '+' || p[n] == '.' || p[n] == 'e' || p[n] == 'E')) {
+                tmp[n] = p[n];
+                ++n;
+            }
+            tmp[n] = '\0';
             char *end = nullptr;
-            v.num = strtod(p, &end);
-            if (end == p || end > e) err("bad number");
+            v.num = strtod(tmp, &end);
+            if (n == 0 || end == tmp) err("bad number");
             v.t = JVal::Num;
-            p = end;
+            p += (end - tmp);
         }
         return v;
     }
