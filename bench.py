@@ -161,30 +161,48 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_port_decode_sample(n_tokens: int, threads: int):
-    """Oracle port, bounded sample: n single-token decode steps (26 layers + lm_head) of one stream
-    with the full-size weights, all host threads.  Returns (tokens/s, seconds)."""
+def cpu_port_decode_sample(n_steps: int, threads: int, streams: int = 1, with_prefill: bool = False):
+    """Oracle port, bounded sample of the GPU arm's decode workload: `streams` concurrent streams batched exactly as the
+    GPU batches them (every weight matrix swept ONCE per step for all streams; attention per stream), optionally the
+    38-token prefill of all streams, then `n_steps` single-token steps (26 layers + tied lm_head + argmax) with the
+    full-size weights on all host threads.  Returns dict(prefill_s, step_s, steps, streams).
+    Timed with the vectorised (AVX2 + FMA) re-association of the port (oracle/q4_fast.c), not the strict shader-order
+    loop the parity tests use: the baseline should be what these cores can do."""
     import torch
     from oracle import mel as omel, q4 as oq4
-    from oracle.model import OracleModel
-    torch.set_num_threads(1)   # the torch ops at M=1 are tiny; the Q4 matvec (C, OpenMP) gets the cores
-    # timed with the vectorised (AVX2 + FMA) re-association of the port, not the strict shader-order loop the
-    # parity tests use: the baseline should be what these cores can do (oracle/q4_fast.c)
+    from oracle.model import OracleModel, PREFIX_LEN
+    torch.set_num_threads(threads if with_prefill else 1)   # M=1..8 torch ops are tiny; the prefill GEMMs want the cores
     oq4.FAST = True
     om = OracleModel(GGUF_PATH, threads=threads)
     cfg = om.cfg
     ada = om.ada_scales(omel.time_embedding(6.0, cfg.dec_dim))
-    cache = om.new_cache()
-    tok = 1
-    # one untimed step (page-faults the mmapped weights)
-    h = om.decoder_forward_with_cache(om.embed_tokens([tok]), ada, cache)
-    tok = int(torch.argmax(om.lm_head(h)[0]))
+    caches = [om.new_cache() for _ in range(streams)]
+    prefill_s = 0.0
+    if with_prefill:
+        prefix = [1] + [32] * (PREFIX_LEN - 1)
+        x = torch.cat([om.embed_tokens(prefix) for _ in range(streams)])
+        t0 = time.perf_counter()
+        h = om.decoder_forward_batched(x, ada, caches, PREFIX_LEN)
+        last = h.reshape(streams, PREFIX_LEN, -1)[:, -1]
+        toks = [int(t) for t in torch.argmax(om.lm_head(last), dim=1)]
+        prefill_s = time.perf_counter() - t0
+        torch.set_num_threads(1)
+    else:
+        toks = [1] * streams
+        h = om.decoder_forward_batched(torch.cat([om.embed_tokens([t]) for t in toks]), ada, caches, 1)   # untimed: faults the weights in
+        toks = [int(t) for t in torch.argmax(om.lm_head(h), dim=1)]
     t0 = time.perf_counter()
-    for _ in range(n_tokens):
-        h = om.decoder_forward_with_cache(om.embed_tokens([tok]), ada, cache)
-        tok = int(torch.argmax(om.lm_head(h)[0]))
+    for _ in range(n_steps):
+        h = om.decoder_forward_batched(torch.cat([om.embed_tokens([t]) for t in toks]), ada, caches, 1)
+        toks = [int(t) for t in torch.argmax(om.lm_head(h), dim=1)]
     dt = time.perf_counter() - t0
-    return n_tokens / dt, dt
+    return {"prefill_s": prefill_s, "step_s": dt / max(n_steps, 1), "steps": n_steps, "streams": streams, "seconds": dt + prefill_s}
+
+
+def cpu_decode_tokens_per_sec(sample: dict, tokens_per_stream: int = 108) -> float:
+    """The metric's definition (e2e_bench.rs:231-240: tokens / decode seconds, prefill included) evaluated on the
+    sampled prefill time + per-step time: tokens_per_stream * streams / (prefill + (tokens_per_stream - 1) * step)."""
+    return tokens_per_stream * sample["streams"] / (sample["prefill_s"] + (tokens_per_stream - 1) * sample["step_s"])
 
 
 def cpu_threads() -> int:
@@ -193,31 +211,77 @@ def cpu_threads() -> int:
 
 
 def run_reference(args, rank, world):
+    """The reference's own CPU implementation does not exist (Rust + wgpu only): the oracle port is timed,
+    on the SAME workload as our arm -- `--streams` (8) concurrent 16 s streams batched per weight sweep, 38-token
+    prefill + single-token steps -- each step a bounded sample (one prefill + 3 decode steps) evaluated with the
+    metric's own definition.  Rank 0 only."""
     if rank != 0:
         return
     ensure_gguf(0, lambda: None)
     threads = cpu_threads()
-    per_step = 2
-    for _ in range(args.warmup):
-        cpu_port_decode_sample(1, threads)
-        break  # one warm-up pass is enough to fault the weights in; W is honoured as >=1
-    vals, t_all = [], 0.0
+    B = args.streams
+    cpu_port_decode_sample(1, threads, streams=B)      # warm-up: faults the 2.5 GB of weights in (W honoured as >= 1)
+    vals, t_all, pf, st = [], 0.0, 0.0, 0.0
     for _ in range(args.steps):
-        v, dt = cpu_port_decode_sample(per_step, threads)
-        vals.append(v)
-        t_all += dt
-    value = per_step * args.steps / t_all
-    sample = f"{per_step} single-token decode steps of 1 stream per step (full-size synthetic weights, f32, AVX2 port, no batching)"
+        smp = cpu_port_decode_sample(3, threads, streams=B, with_prefill=True)
+        vals.append(cpu_decode_tokens_per_sec(smp))
+        t_all += smp["seconds"]
+        pf += smp["prefill_s"]
+        st += smp["step_s"]
+    K = args.steps
+    value = 108 * B / (pf / K + 107 * st / K)
+    sample = (f"per step: 38-token prefill of {B} streams + 3 batched single-token decode steps ({B} streams per weight sweep), "
+              f"full-size synthetic weights, f32, AVX2 port; tokens/s = 108*{B} / (prefill {pf / K:.2f} s + 107 x step {st / K * 1e3:.0f} ms)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * t_all / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Voxtral-Mini-4B Q4_0 decode, 16 s audio (bounded CPU sample of the same decode step)",
+        "config": {"workload": f"configs[4]: {B} concurrent 16 s streams per GPU, decode (38-token prefill + 107 steps -> 108 tokens/stream); "
+                               "bounded CPU sample of the same batched workload",
+                   "model": "Voxtral-Mini-4B-Realtime Q4_0 GGUF layout, synthetic weights (seed 42)",
+                   "audio_seconds": AUDIO_SECONDS, "streams_per_gpu": B, "tokens_per_stream": 108,
                    "note": "reference cannot be built here (Rust; no CPU backend at this commit): oracle port timed"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def streaming_leg(vx, model, audio, B, max_ticks=260):
+    """B live sessions, each fed 1280 samples (80 ms) per tick, all opened together (worst case: every session steps in
+    every second tick).  Returns per-tick device latency statistics and the real-time headroom."""
+    pool = vx.StreamingPool(model, max_sessions=B, max_seconds=20.0)
+    try:
+        peak = np.abs(audio).max(axis=1, keepdims=True)
+        sig = (audio * (0.95 / np.maximum(peak, 1e-10))).astype(np.float32)
+        sids = [pool.open() for _ in range(B)]
+        n = sig.shape[1]
+        ticks_ms, steps, out = [], 0, [[] for _ in range(B)]
+        first = pool.tick()                      # the left padding (6.08 s of silence): encoder backlog + prefill
+        fed = 0
+        while fed < n and len(ticks_ms) < max_ticks:
+            for i, sid in enumerate(sids):
+                pool.push(sid, sig[i, fed:fed + 1280])
+            st = pool.tick()
+            ticks_ms.append(st["gpu_ms"])
+            steps += st["decode_steps"]
+            fed += 1280
+        for sid in sids:
+            pool.finish(sid)
+        last = pool.tick()
+        for i, sid in enumerate(sids):
+            out[i] = pool.poll(sid)[0]
+        t = np.array(ticks_ms)
+        return {"sessions": B, "tick_audio_ms": 80.0, "ticks": int(t.size), "tick_gpu_ms_mean": float(t.mean()),
+                "tick_gpu_ms_p50": float(np.percentile(t, 50)), "tick_gpu_ms_p95": float(np.percentile(t, 95)),
+                "tick_gpu_ms_max": float(t.max()), "open_tick_gpu_ms": first["gpu_ms"], "finish_tick_gpu_ms": last["gpu_ms"],
+                "decode_steps": int(steps), "tokens_per_session": len(out[0]),
+                "realtime_factor": float(t.mean() / 80.0),
+                "sessions_at_realtime_estimate": int(B * 80.0 / max(float(np.percentile(t, 95)), 1e-6)),
+                "note": "device time per 80 ms tick for all sessions (incremental mel+conv, 32 encoder layers over K/V rings, adapter, "
+                        "one shared paged-KV decoder step every 2nd tick); estimate = sessions x 80 ms / p95 tick"}
+    finally:
+        pool.close()
 
 
 # --------------------------------------------------------------------------------------------
@@ -300,24 +364,47 @@ def run_ours(args, rank, local_rank, world):
         model.transcribe_pcm_dev(dev_audio, 1, n, timings=tm1)
         s_dec += tm1.decode_ms; s_tot += tm1.total_ms; s_pf += tm1.prefill_ms
     s_step_ms = (s_dec - s_pf) / K / max(n_tok - 1, 1)
+    # single-stream end to end through the host-buffer C ABI (pinned PCM in, ids out)
+    model.transcribe_pcm(pinned.array[0], timings=tm1)
+    vx.lib().vox_dev_sync(local_rank)
+    e1 = time.perf_counter()
+    for _ in range(K):
+        model.transcribe_pcm(pinned.array[0], timings=tm1)
+    s_e2e_wall = time.perf_counter() - e1
     single = {"decode_tokens_per_sec": n_tok * K / (s_dec / 1e3), "rtf": (s_tot / K / 1e3) / AUDIO_SECONDS,
+              "e2e": {"tokens_per_sec": n_tok * K / s_e2e_wall, "rtf": (s_e2e_wall / K) / AUDIO_SECONDS,
+                      "h2d_bytes_per_step": int(n * 4), "d2h_bytes_per_step": int(n_tok * 4),
+                      "definition": "108 tokens / wall time of vox_transcribe_pcm for one stream (whole pipeline)"},
               "decode_ms": s_dec / K, "total_ms": s_tot / K, "prefill_ms": s_pf / K, "ms_per_decode_step": s_step_ms,
               "published_gb10_tokens_per_sec": 19.4, "published_gb10_rtf": 0.416}
 
-    # ---- isolated Q4 matvec (configs[1]): [1,3072] x [9216,3072]^T, 24 rotating weight copies
+    # ---- isolated Q4 matvec (configs[1]): [1,3072] x [N,3072]^T for N = 9216 (the reference's bench shape,
+    # benches/q4_ops.rs:57-65) and N = 8192 (BASELINE.json's stated shape), 24 rotating weight copies each
     mv = None
     try:
         from voxtral_mini_realtime_rs_b200 import synth
-        kk, nn = 3072, 9216   # dec_ffn_w1_1tok (benches/q4_ops.rs:57-65)
-        raw = synth.random_q4_blocks(np.random.Generator(np.random.PCG64(7)), nn * kk, 0.02)
-        ws = [vx.Q4Tensor.from_q4_bytes(raw, (nn, kk), local_rank) for _ in range(24)]
-        ms = vx.q4_matmul_bench(ws, 1, iters=480, warmup=48)
-        mv_bytes = nn * kk * 18 // 32 + 4 * kk + 4 * nn
-        mv = {"shape": "[1,3072]x[9216,3072]^T", "ms": ms, "bytes": mv_bytes, "gbs": mv_bytes / ms / 1e6,
-              "l2": "24 rotating weight copies (382 MB) > 126 MB L2"}
-        del ws
+        mv = {}
+        for nn in (9216, 8192):
+            kk = 3072
+            raw = synth.random_q4_blocks(np.random.Generator(np.random.PCG64(7)), nn * kk, 0.02)
+            ws = [vx.Q4Tensor.from_q4_bytes(raw, (nn, kk), local_rank) for _ in range(24)]
+            ms = vx.q4_matmul_bench(ws, 1, iters=480, warmup=48)
+            mv_bytes = nn * kk * 18 // 32 + 4 * kk + 4 * nn
+            mv[f"n{nn}"] = {"shape": f"[1,3072]x[{nn},3072]^T", "ms": ms, "bytes": mv_bytes, "gbs": mv_bytes / ms / 1e6,
+                            "l2": f"24 rotating weight copies ({24 * mv_bytes / 1e6:.0f} MB) > 126 MB L2"}
+            del ws
+        mv.update(mv["n9216"])      # top-level keys = the reference's shape (as in round 1)
     except Exception as e:  # pragma: no cover
         mv = {"error": str(e)}
+
+    # ---- streaming sessions: `B` live sessions fed 80 ms per tick through vox_stream_*; per-tick
+    # device latency and how many such sessions one GPU sustains at real time (tick budget = 80 ms of audio)
+    streaming = None
+    if not args.no_streaming:
+        try:
+            streaming = streaming_leg(vx, model, audio, B)
+        except Exception as e:  # pragma: no cover
+            streaming = {"error": str(e)}
 
     if rank != 0:
         return
@@ -332,7 +419,9 @@ def run_ours(args, rank, local_rank, world):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                "traffic_source": "static: profiles/traffic.json (ncu --set full capture of this kernel; not re-measured in this run)",
+                "peak_source": peak_src,
                 "launch": f"one decode step for B={B} streams = one launch of the persistent decode kernel (CUDA-graph replay)",
                 "algorithmic_bytes_per_launch": step_bytes, "ms_per_launch": step_ms_loop,
                 "single_stream": {"achieved": step_bytes / (s_step_ms / 1e3) / 1e9,
@@ -343,9 +432,11 @@ def run_ours(args, rank, local_rank, world):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = cpu_threads()
-        v, dt = cpu_port_decode_sample(args.cpu_tokens, threads)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_tokens} single-token decode steps of 1 stream, full-size weights, AVX2 port ({dt:.1f} s)"}
+        smp = cpu_port_decode_sample(args.cpu_tokens, threads, streams=B, with_prefill=True)
+        cpu = {"value": cpu_decode_tokens_per_sec(smp, int(n_tok)), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"38-token prefill of {B} streams ({smp['prefill_s']:.1f} s) + {args.cpu_tokens} batched single-token decode steps "
+                         f"({smp['step_s'] * 1e3:.0f} ms/step, {B} streams per weight sweep), full-size weights, AVX2 port; "
+                         f"tokens/s by the metric's definition: {int(n_tok)}*{B} / (prefill + {int(n_tok) - 1} steps)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -364,7 +455,7 @@ def run_ours(args, rank, local_rank, world):
                 "definition": "tokens / wall time of vox_transcribe_pcm (pinned host PCM in, ids out)",
                 "ids_match_device_path": same},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "single_stream": single,
+        "single_stream": single, "streaming": streaming,
         # encoder + adapter of the same streams, algorithmic 1.235 TFLOP per 16 s stream
         # (f32-equivalent; the tcgen05 GEMM spends 5 bf16 MMAs per product for f32-grade accuracy)
         "encoder": {"ms": enc_ms / K, "algorithmic_tflop": 1.235 * B,
@@ -383,7 +474,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--streams", type=int, default=8, help="concurrent 16 s streams per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-tokens", type=int, default=24)
+    ap.add_argument("--cpu-tokens", type=int, default=6)
+    ap.add_argument("--no-streaming", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()

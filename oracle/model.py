@@ -307,6 +307,40 @@ class OracleModel:
                 capture[f"dec{j}"] = x.clone()
         return rms_norm(x, self.f32(FINAL_NORM), c.norm_eps)
 
+    def decoder_forward_batched(self, x: torch.Tensor, ada, caches, rows_per_stream: int = 1) -> torch.Tensor:
+        """forward_hidden_with_cache (model.rs:665-677) for B independent streams in ONE weight sweep: x
+        [B*rows_per_stream, D] (stream-major), caches = one LayerCaches per stream.  Every linear sees all rows at once
+        (the weights are read once for the whole batch, as the GPU path does); attention stays per stream.  Same
+        arithmetic per row as decoder_forward_with_cache -- used by bench.py's CPU arm so that the CPU baseline runs the
+        SAME batched workload as the GPU arm."""
+        c = self.cfg
+        m = rows_per_stream
+        nb = x.shape[0] // m
+        scale = float(np.float32(c.dec_head_dim) ** np.float32(-0.5))
+        for j in range(c.dec_layers):
+            p = f"layers.{j}"
+            h = rms_norm(x, self.f32(f"{p}.attention_norm.weight"), c.norm_eps)
+            q = self.linear(h, f"{p}.attention.wq.weight")
+            k = self.linear(h, f"{p}.attention.wk.weight")
+            v = self.linear(h, f"{p}.attention.wv.weight")
+            outs = []
+            for b in range(nb):
+                cache = caches[b]
+                off = 0 if cache[j]["k"] is None else cache[j]["k"].shape[0]
+                sl = slice(b * m, (b + 1) * m)
+                qb = apply_rope(q[sl].reshape(m, c.dec_heads, c.dec_head_dim), self.dec_cos, self.dec_sin, off)
+                kb = apply_rope(k[sl].reshape(m, c.dec_kv_heads, c.dec_head_dim), self.dec_cos, self.dec_sin, off)
+                vb = v[sl].reshape(m, c.dec_kv_heads, c.dec_head_dim)
+                cache[j]["k"] = kb if off == 0 else torch.cat([cache[j]["k"], kb])
+                cache[j]["v"] = vb if off == 0 else torch.cat([cache[j]["v"], vb])
+                outs.append(self._attention(qb, cache[j]["k"], cache[j]["v"], scale, off, c.dec_window))
+            x = self.linear(torch.cat(outs), f"{p}.attention.wo.weight") + x
+            h = rms_norm(x, self.f32(f"{p}.ffn_norm.weight"), c.norm_eps) * ada[j]
+            gate = F.silu(self.linear(h, f"{p}.feed_forward.w1.weight"))
+            up = self.linear(h, f"{p}.feed_forward.w3.weight")
+            x = self.linear(gate * up, f"{p}.feed_forward.w2.weight") + x
+        return rms_norm(x, self.f32(FINAL_NORM), c.norm_eps)
+
     def lm_head(self, h: torch.Tensor) -> torch.Tensor:
         """model.rs:680-691 (tied embeddings)."""
         return self.linear(h, TOK_EMB)

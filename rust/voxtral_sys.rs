@@ -1,15 +1,10 @@
-# INTEGRATION — binding `libvoxtral_b200.so` from the reference crate
-
-The reference (`TrevorS/voxtral-mini-realtime-rs`) has no FFI; its callers use the Rust API listed in
-SURVEY.md §8(b).  `include/voxtral.h` exports a C ABI with one entry point per seam (each prototype
-cites the Rust item it replaces).  No Rust toolchain exists in the build environment, so the shim
-below is **source only — never compiled here**; it is what a maintainer would add as
-`src/b200/sys.rs` + `src/b200/mod.rs` behind a `b200` cargo feature
-(`Cargo.toml`: `b200 = []`, `build.rs`: `println!("cargo:rustc-link-lib=dylib=voxtral_b200")`).
-
-## 1. Raw bindings (`sys.rs`; the full file is `rust/voxtral_sys.rs`)
-
-```rust
+// rust/voxtral_sys.rs -- raw `extern "C"` bindings for include/voxtral.h (libvoxtral_b200.so).
+//
+// SOURCE ONLY: there is no Rust toolchain in the build environment, so this file has never been compiled;
+// it is the `src/b200/sys.rs` a maintainer of TrevorS/voxtral-mini-realtime-rs would add behind a `b200` cargo feature
+// (Cargo.toml: `b200 = []`; build.rs: `println!("cargo:rustc-link-lib=dylib=voxtral_b200")`).  INTEGRATION.md shows the
+// safe wrapper (`mod.rs`) and the call-site changes in src/bin/transcribe.rs.  tests/test_host_abi.py checks that every
+// function declared here is exported by the library with the same name.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_void};
 
@@ -101,99 +96,3 @@ extern "C" {
                                 cap: usize, written: *mut usize) -> i32;
     pub fn vox_tokenizer_free(t: *mut vox_tokenizer);
 }
-```
-
-## 2. Safe wrapper with the crate's own names (`mod.rs`)
-
-```rust
-pub struct Q4VoxtralModel { model: *mut sys::vox_model, sess: *mut sys::vox_session }
-
-fn check(code: i32) -> anyhow::Result<()> {
-    if code == 0 { return Ok(()); }
-    let msg = unsafe { std::ffi::CStr::from_ptr(sys::vox_last_error()) }.to_string_lossy().into_owned();
-    anyhow::bail!("voxtral_b200 error {code}: {msg}")
-}
-
-impl Q4VoxtralModel {
-    /// replaces Q4ModelLoader::from_file(path)?.load(&device)  (src/gguf/loader.rs:82,109)
-    pub fn load(path: &std::path::Path, device: i32, max_mel_frames: i32) -> anyhow::Result<Self> {
-        let c = std::ffi::CString::new(path.to_str().unwrap())?;
-        let (mut m, mut s) = (std::ptr::null_mut(), std::ptr::null_mut());
-        check(unsafe { sys::vox_model_load_gguf(c.as_ptr(), device, &mut m) })?;
-        check(unsafe { sys::vox_session_create(m, 1, max_mel_frames, &mut s) })?;
-        Ok(Self { model: m, sess: s })
-    }
-    /// replaces transcribe_streaming(mel: Tensor<Wgpu,3>[1,128,T], t_embed)  (src/gguf/model.rs:873)
-    /// `mel` is the row-major [128, T] buffer the CLI already builds (transcribe.rs:295-305).
-    pub fn transcribe_streaming(&self, mel: &[f32], t_frames: usize, delay: f32) -> anyhow::Result<Vec<i32>> {
-        check(unsafe { sys::vox_session_set_delay(self.sess, delay) })?;
-        let mut out = vec![0i32; t_frames / 16 + 2];
-        let mut n = 0i32;
-        check(unsafe { sys::vox_transcribe_streaming(self.sess, mel.as_ptr(), 1, t_frames as i32,
-              out.as_mut_ptr(), out.len(), &mut n, std::ptr::null_mut()) })?;
-        out.truncate(n as usize);
-        Ok(out)
-    }
-}
-impl Drop for Q4VoxtralModel {
-    fn drop(&mut self) { unsafe { sys::vox_session_free(self.sess); sys::vox_model_free(self.model); } }
-}
-```
-
-## 3. Call-site changes in `src/bin/transcribe.rs`
-
-* `load_model` (141-160): `ModelState::Q4 { model: b200::Q4VoxtralModel::load(gguf, 0, max_mel_frames + 1150)? }`
-  (1150 = the mel frames added by the 76+17 pad tokens).
-* `transcribe_one` (254-256): `model.transcribe_streaming(&mel_flat, n_frames, delay as f32)?` with the
-  `mel_flat` vector it already computes — or skip the CPU mel entirely with `vox_transcribe_pcm`
-  (device-side peak-normalise + pad + mel), passing the chunk's samples.
-* `TimeEmbedding`/`t_embed` tensors disappear (`vox_session_set_delay` computes the embedding and the 26
-  ADA vectors once).
-* Everything else (WAV IO, resampling, chunking, tokenizer, clap flags) is unchanged; the tokenizer may
-  stay in Rust or use `vox_tokenizer_*`.
-
-`src/bin/e2e_bench.rs:138-254` maps the same way; `vox_timings` carries its `preprocess/encode/decode`
-split (device-timed with CUDA events).
-
-## 3b. Streaming sessions (the crate's unused `encode_audio_with_cache` / `forward_with_cache`, model.rs:790-867)
-
-```rust
-// one pool per GPU worker; sessions = live microphones / sockets
-let mut pool = std::ptr::null_mut();
-check(unsafe { sys::vox_stream_pool_create(model.model, 32, 30.0, &mut pool) })?;
-let mut sid = 0;  check(unsafe { sys::vox_stream_open(pool, &mut sid) })?;
-loop {                                             // every 80 ms (or whenever audio arrives)
-    check(unsafe { sys::vox_stream_push_pcm(pool, sid, chunk.as_ptr(), chunk.len()) })?;
-    check(unsafe { sys::vox_stream_tick(pool, std::ptr::null_mut()) })?;          // all sessions advance together
-    let (mut n, mut done) = (0usize, 0i32);
-    check(unsafe { sys::vox_stream_poll_ids(pool, sid, ids.as_mut_ptr(), ids.len(), &mut n, &mut done) })?;
-    emit(tokenizer.decode(&ids[..n]));             // tokens of positions whose audio is final
-}
-// end of utterance: vox_stream_finish(pool, sid); one more tick; poll until done != 0; vox_stream_close
-```
-The ids equal `transcribe_streaming`'s for the same (peak-normalised) audio; `vox_decode_step` /
-`vox_prefill` are the device-side forms of `generate_step_with_cache` for callers that drive the decoder themselves.
-
-## 4. What a Python caller does today (used by the tests and the bench)
-
-```python
-import voxtral_mini_realtime_rs_b200 as vx
-model = vx.Q4ModelLoader.from_file("voxtral-q4.gguf").load(device=0, max_batch=8, max_mel_frames=2400)
-ids = model.transcribe_pcm(samples)          # [B, n] f32 16 kHz -> int32 [B, n_tokens]
-text = vx.VoxtralTokenizer.from_file("tekken.json").decode([t for t in ids[0] if t >= 1000])
-```
-
-## 5. Runtime switches (environment, read at session creation; all default to the fast path)
-
-| variable | effect |
-|---|---|
-| `VOX_MEGA=0` | per-op decode launches instead of the persistent decode-step kernel |
-| `VOX_MEGA_MIN_B=n` | smallest batch that uses the persistent kernel (default 2; a single stream is served by the per-op path) |
-| `VOX_ENC_ATTN=simt` | f32 SIMT encoder attention instead of the tensor-core kernel |
-| `VOX_GEMM=simt` | SIMT tiled GEMM instead of the tcgen05 GEMM (encoder / prefill) |
-| `VOX_MATVEC=simt` | SIMT Q4 matvec instead of the tensor-core matvec (per-op decode path) |
-| `VOX_PDL=0` | no programmatic dependent launch between the per-op decode kernels |
-
-They exist for cross-checking (every alternative path is parity-tested against the oracle) and for bisecting
-on new hardware; `vox_session_debug_read(s, "<name>_on|_off", ...)` flips the same switches at run time.
-There is no CPU fallback behind any of them.

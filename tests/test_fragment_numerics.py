@@ -90,3 +90,36 @@ def test_tiny_and_huge_magnitudes():
     for mag in (1e-30, 1e-12, 1e12, 1e28):
         em, _ = _case((rng.standard_normal(1024) * mag).astype(F32), seed=7)
         assert em.max() < 4e-7, mag
+
+
+def test_gemm_f16_two_by_two_split_three_products():
+    """numpy model of the tcgen05 GEMM's operand split (csrc/gemm_tc5.cu, round 2): weights (q-8)*d*2^8 as f16 hi + the
+    exact f16 residual, activations * 2^s_t as f16 hi + mid, products w_hi x_h + w_hi x_m + w_lo x_h in f64 (the MMA
+    accumulates in f32).  Error relative to sum |w||x| stays at the f32 rounding level even with outlier activations and
+    tiny / large block scales -- i.e. 3 MMAs per k-step carry f32-grade accuracy (round 1 spent 5 on bf16 pieces)."""
+    rng = np.random.default_rng(0)
+    K, N, M = 5120, 48, 12
+    for dscale in (1e-4, 1e-2, 3.0):
+        d = (rng.uniform(0.5, 1.5, (N, K // 32)) * dscale).astype(np.float16)
+        n8 = (rng.integers(0, 16, (N, K)) - 8).astype(np.float64)
+        w = n8 * np.repeat(d.astype(np.float64), 32, 1)
+        x = (rng.standard_normal((M, K)) * rng.uniform(0.01, 30, (M, 1))).astype(np.float32)
+        x[:, ::97] *= 50.0
+        d2 = np.repeat((d.astype(np.float32) * 256).astype(np.float16), 32, 1).astype(np.float64)
+        hi = (n8 * d2).astype(np.float16)                                  # HMUL2: RN_f16(n8 * d')
+        lo = (n8 * d2 - hi.astype(np.float64)).astype(np.float16)          # HFMA2: the residual
+        assert np.all(np.isfinite(hi.astype(np.float64)))
+        if dscale >= 1e-2:                                                 # normal range: the split is exact
+            assert np.array_equal(hi.astype(np.float64) + lo.astype(np.float64), n8 * d2)
+        mx = np.abs(x).max(1) * 1.0001
+        sc = 2.0 ** (7 - np.floor(np.log2(mx)))[:, None]
+        xs = x.astype(np.float64) * sc
+        xh = xs.astype(np.float16)
+        xm = (xs - xh.astype(np.float64)).astype(np.float16)
+        assert np.all(np.isfinite(xh.astype(np.float64))) and np.abs(xs).max() < 256.0
+        got = (xh.astype(np.float64) @ hi.astype(np.float64).T + xm.astype(np.float64) @ hi.astype(np.float64).T
+               + xh.astype(np.float64) @ lo.astype(np.float64).T) / sc / 256.0
+        exact = x.astype(np.float64) @ w.T
+        den = np.abs(x.astype(np.float64)) @ np.abs(w).T
+        err = float((np.abs(got - exact) / den).max())
+        assert err < 2.0 ** -22, (dscale, err)

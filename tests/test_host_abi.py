@@ -220,3 +220,14 @@ def test_tokenizer_unicode_escapes(vx):
     assert t.decode([1001]) == o.decode([1001]) == "café 😀"
     assert t.decode([1002]) == o.decode([1002]) == "fb"      # invalid base64 -> token_str fallback
     assert t.decode_token(0) == "<s>"
+
+
+def test_rust_binding_names_are_exported(vx):
+    """rust/voxtral_sys.rs (source-only FFI binding for the reference crate) declares only functions the library exports."""
+    import re
+    src = open(os.path.join(ROOT, "rust", "voxtral_sys.rs")).read()
+    names = re.findall(r"pub fn (vox_\w+)\(", src)
+    assert len(names) > 40
+    lib = vx.lib()
+    for n in names:
+        assert hasattr(lib, n), n

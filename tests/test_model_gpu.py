@@ -180,6 +180,28 @@ def test_transcribe_pcm_pipeline_and_batch(vx, tiny_model, tiny_oracle):
         assert tiny_model.transcribe_pcm(sigs[i])[0].tolist() == exp[i]
 
 
+def test_batches_above_eight_streams(vx, tiny_gguf, tiny_oracle):
+    """More than 8 streams per GPU leave the persistent decode kernel (token capacity 8) for the per-op path whose
+    linears are the tcgen05 GEMM (M = B > 8 rows) -- same ids as the oracle, graph replay == eager."""
+    m = vx.Q4ModelLoader.from_file(tiny_gguf).load(0, max_batch=20, max_mel_frames=1500)
+    try:
+        sigs = [omel.speechlike(3.0, seed=300 + i) for i in range(20)]
+        t_embed = omel.time_embedding(6.0, tiny_oracle.cfg.dec_dim)
+        exp = [tiny_oracle.transcribe_streaming(omel.mel_tensor_from_audio(omel.peak_normalize(s)), t_embed) for s in sigs]
+        for b in (9, 12, 20):
+            got = m.transcribe_pcm(np.stack(sigs[:b]))
+            assert got.shape == (b, len(exp[0]))
+            for i in range(b):
+                assert got[i].tolist() == exp[i], (b, i)
+        m.debug("graph_off")
+        got = m.transcribe_pcm(np.stack(sigs[:12]))
+        m.debug("graph_on")
+        for i in range(12):
+            assert got[i].tolist() == exp[i], i
+    finally:
+        m.close()
+
+
 def test_generate_step_with_cache_parity(tiny_model, tiny_oracle):
     """Incremental API (model.rs:857-867): prefill M=5 then single steps; logits vs oracle."""
     cfg = tiny_oracle.cfg

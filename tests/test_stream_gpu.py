@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def tiny_model(vx, tiny_gguf):
-    m = vx.Q4ModelLoader.from_file(tiny_gguf).load(0, max_batch=1, max_mel_frames=1000)
+    m = vx.Q4ModelLoader.from_file(tiny_gguf).load(0, max_batch=1, max_mel_frames=1500)
     yield m
     m.close()
 
@@ -62,7 +62,7 @@ def test_sessions_of_different_ages_share_the_pool(vx, tiny_model, tiny_oracle, 
     audios = [omel.peak_normalize(omel.speechlike(float(rng.uniform(2.0, 4.5)), 100 + i)) for i in range(n_sessions)]
     wants = [_offline(tiny_oracle, a)[0] for a in audios]
     pool = vx.StreamingPool(tiny_model, max_sessions=n_sessions, max_seconds=8.0)
-    start = [5 * i for i in range(n_sessions)]              # tick at which each session opens
+    start = [4 * i for i in range(n_sessions)]              # tick at which each session opens (a session steps every 2nd tick)
     sids = [None] * n_sessions
     fed = [0] * n_sessions
     got = [[] for _ in range(n_sessions)]
@@ -110,7 +110,8 @@ def test_pool_capacity_and_errors(vx, tiny_model):
         pool.push(sid, np.zeros(10, np.float32))
     pool.tick()
     ids, done = pool.poll(sid)
-    assert done and ids == []                   # no audio: 93 padding tokens -> 23 positions < 38 -> no ids (model.rs:887-889)
+    # no audio at all: the stream is the 76 + 17 padding tokens = 119 040 samples -> 46 positions -> 8 ids (model.rs:883-963)
+    assert done and len(ids) == vx.stream_progress(119040, True)[4] == 8
     pool.close_session(sid)
     sid2 = pool.open()
     assert sid2 == sid

@@ -28,12 +28,14 @@ dec_attn_fused_kernel(const float *__restrict__ qkv, const int ld, const int H, 
     __shared__ float kvs[2][HD];
     __shared__ float red_m[DA_WARPS][G], red_l[DA_WARPS][G];
     __shared__ float red_acc[DA_WARPS][G][HD];
+    __shared__ int pts[64];  // this row's page table (first 64 logical pages = 1024 positions; beyond: global)
     // let the next kernel (the wo matvec) start prefetching its weights while we run
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const int kvh = blockIdx.x, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pos = kv.pos[b];
     if (pos >= kv.max_seq()) return;
+    for (int i = threadIdx.x; i < 64 && i < kv.max_pages; i += DA_THREADS) pts[i] = kv.page_table[(size_t)b * kv.max_pages + i];
     const float *row = qkv + (size_t)b * ld;  // M = 1: one row per stream
     // ---- load q (G heads), k, v of this group; RoPE q and k; append k, v at `pos`
     for (int i = threadIdx.x; i < G * HD; i += DA_THREADS) qs[i / HD][i % HD] = row[(kvh * G + i / HD) * HD + i % HD];
@@ -77,7 +79,9 @@ dec_attn_fused_kernel(const float *__restrict__ qkv, const int ld, const int H, 
     const int j_lo = pos - window > 0 ? pos - window : 0;
     for (int j = j_lo + warp; j <= pos; j += DA_WARPS) {
         float kk[DPL], vv[DPL];
-        const size_t at = kv_index(kv, b, Hkv, kvh, j, HD) + lane * DPL;
+        const int pg = j / KV_PAGE;
+        const int phys = pg < 64 ? pts[pg] : kv.page_table[(size_t)b * kv.max_pages + pg];
+        const size_t at = (((size_t)phys * Hkv + kvh) * KV_PAGE + (j % KV_PAGE)) * HD + lane * DPL;
         const float *kr = kv.k + at;
         const float *vr = kv.v + at;
 #pragma unroll

@@ -523,11 +523,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                     // share one read of the activation fragments
                     for (int it = 0; it < ntl; it += NT) {
                         const int nt = min(NT, ntl - it);
+#ifdef VOX_MEGA_WARP_TRACE
                         // warp-level trace of the lm_head phase's first groups (CTA 0; debug "mega_trace_w")
                         unsigned long long *tw = nullptr;
                         if (p.trace_w != nullptr && cta == 0 && lane == 0 && oi == p.n_ops - 2 && s == 0 && it / NT < 6)
                             tw = p.trace_w + ((size_t)warp * 6 + it / NT) * 8;
                         if (tw) tw[0] = (unsigned long long)clock64();
+#else
+                        constexpr unsigned long long *tw = nullptr;   // compile with -DVOX_MEGA_WARP_TRACE to record
+#endif
                         float acc[NT][2 * CG];
 #pragma unroll
                         for (int u = 0; u < NT; ++u)
@@ -616,8 +620,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                             float v = 0.0f;
                             if (r_valid) {
                                 const float *rp = red + (size_t)par * MG_CWARPS * (NT * 16 * MT) + rt;
+                                // fixed-shape tree over the 16 warps' partials: all loads in flight at once, depth-4 adds
+                                float pw[MG_CWARPS];
 #pragma unroll
-                                for (int w = 0; w < MG_CWARPS; ++w) v += rp[w * (NT * 16 * MT)];
+                                for (int w = 0; w < MG_CWARPS; ++w) pw[w] = rp[w * (NT * 16 * MT)];
+#pragma unroll
+                                for (int st = 1; st < MG_CWARPS; st <<= 1)
+#pragma unroll
+                                    for (int w = 0; w < MG_CWARPS; w += 2 * st) pw[w] += pw[w + st];
+                                v = pw[0];
                                 if (S > 1) {
                                     float *at = acc_tile + (size_t)(it + r_slot) * 16 * MT + (rt % (16 * MT));
                                     if (s > 0) v += *at;

@@ -2,12 +2,15 @@
 // encoder / prefill sized problems:   Y[M_tok, N] = X[M_tok, K] . W[N, K]^T  (+ epilogue).
 // Reference arithmetic: src/gguf/shader_naive.wgsl:31-98 (w = (q-8)*d in f32, f32 accumulate).
 //
-// f32-grade accuracy on bf16 tensor cores ("3 x 2 split"): tcgen05 has no f32-input MMA, so
-//   w = w_hi + w_lo            exact: (q-8)*d has <= 15 significant bits = two bf16 pieces
-//   x = x_h + x_m + x_l        exact: 24 bits = three bf16 pieces
-// and the product is accumulated in f32 TMEM from the five largest terms
-//   w_hi x_h + w_hi x_m + w_lo x_h + w_hi x_l + w_lo x_m        (dropped: w_lo x_l ~ 2^-24 |w||x|)
-// i.e. 5 kind::f16 MMAs per 16-wide K step.  Measured against the oracle in tests/.
+// f32-grade accuracy on f16 tensor cores ("2 x 2 split, 3 products"): tcgen05 has no f32-input MMA, so
+//   w * 2^8  = w_hi + w_lo     f16 pieces, exact: (q-8)*d has <= 14 significant bits; hi = RN_f16((q-8)*d'), lo = the exact
+//                              residual of that rounding -- both produced by two half2 FMA-pipe instructions per weight pair
+//                              (HMUL2, HFMA2), no float conversions (d' = d * 2^8 keeps lo out of the subnormal range)
+//   x * 2^s_t = x_h + x_m      f16 pieces, 22 bits; s_t = per-token power of two that puts the row maximum in [2^7, 2^8)
+// and the product is accumulated in f32 TMEM from the three largest terms
+//   w_hi x_h + w_hi x_m + w_lo x_h            (dropped: w_lo x_m ~ 2^-22 |w||x|, the f32 rounding level)
+// i.e. 3 kind::f16 MMAs per 16-wide K step (round 1 used bf16 pieces: 3 x 2 pieces, 5 MMAs, and ~3x the dequant ALU work).
+// The epilogue multiplies token column t by 2^-(s_t + 8).  Measured against the oracle in tests/.
 //
 // "Swap-AB" tiling: the UMMA M dimension (128 TMEM lanes) runs over output features, the UMMA N
 // dimension (128 TMEM columns) over tokens, so a CTA owns Y[tok0:tok0+128, f0:f0+128]^T:
@@ -39,9 +42,11 @@ constexpr int G5_BN = 128;   // tokens per CTA (UMMA N)
 constexpr int G5_BK = 64;    // K per pipeline stage
 constexpr int G5_TILE_BYTES = G5_BM * G5_BK * 2;          // 16 KB: one bf16 operand tile
 constexpr int G5_STAGES = 2;                              // weight stages (w_hi, w_lo), dequantised in-kernel
-constexpr int G5_XSTAGES = 3;                             // activation stages (x_h, x_m, x_l), fetched one k-step ahead
+constexpr int G5_XSTAGES = 3;                             // activation stages (x_h, x_m), fetched one k-step ahead
 constexpr int G5_WSTAGE_BYTES = 2 * G5_TILE_BYTES;
-constexpr int G5_XSTAGE_BYTES = 3 * G5_TILE_BYTES;
+constexpr int G5_XPIECES = 2;
+constexpr int G5_XSTAGE_BYTES = G5_XPIECES * G5_TILE_BYTES;
+constexpr float G5_WSCALE = 256.0f;                       // weights enter the MMA times 2^8 (see header)
 constexpr int G5_SMEM_BYTES = G5_STAGES * G5_WSTAGE_BYTES + G5_XSTAGES * G5_XSTAGE_BYTES;  // 208 KB
 constexpr int G5_TMEM_COLS = 128;
 
@@ -84,11 +89,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
     d |= (uint64_t)1 << 46;
     return d;
 }
-// instruction descriptor for kind::f16: D = f32, A = B = bf16, both K-major, M x N tile
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor for kind::f16: D = f32 (bit 4), A = B = f16 (format fields 0), both K-major, M x N tile
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -105,7 +110,8 @@ struct G5Args {
     const uint4 *qs;      // row-major Q4 planes (kernels.h Q4Weight)
     const __half *ds;
     int N, K, M;          // M = tokens
-    const __nv_bfloat16 *xt;  // [3][TT][KC][8][128][8] tiled splits of X (zero padded rows)
+    const __half *xt;         // [2][TT][KC][8][128][8] tiled f16 splits of X * 2^s_t (zero padded rows)
+    const float *oscale;      // [TT*128] per-token output scale 2^-(s_t + 8)
     int TT, KC;
     float *y;
     int ldy;
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_d = tmem_base_smem;
-    const uint32_t idesc = umma_idesc_bf16(G5_BM, G5_BN);
+    const uint32_t idesc = umma_idesc_f16(G5_BM, G5_BN);
     const size_t xt_piece = (size_t)a.TT * a.KC * (G5_TILE_BYTES / 2);  // elements per split piece
     const int kc_begin = blockIdx.z * a.KCs, kc_end = min(a.KC, kc_begin + a.KCs);
     unsigned char *xs_base = smem + (size_t)G5_STAGES * G5_WSTAGE_BYTES;
@@ -154,10 +160,10 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
         if (lane == 0) {
             auto fetch_x = [&](int kc_f) {  // the three split pieces of X for k-step kc_f
                 const int xs = (kc_f - kc_begin) % G5_XSTAGES;
-                mbar_expect_tx(&full_bar[xs], 3 * G5_TILE_BYTES);
+                mbar_expect_tx(&full_bar[xs], G5_XPIECES * G5_TILE_BYTES);
 #pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    const __nv_bfloat16 *src = a.xt + p * xt_piece + ((size_t)tt * a.KC + kc_f) * (G5_TILE_BYTES / 2);
+                for (int p = 0; p < G5_XPIECES; ++p) {
+                    const __half *src = a.xt + p * xt_piece + ((size_t)tt * a.KC + kc_f) * (G5_TILE_BYTES / 2);
                     bulk_g2s(xs_base + (size_t)xs * G5_XSTAGE_BYTES + p * G5_TILE_BYTES, src, G5_TILE_BYTES, &full_bar[xs]);
                 }
             };
@@ -180,13 +186,10 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
                     const uint64_t wlo = umma_desc(base + 1 * G5_TILE_BYTES + koff, lbo, sbo);
                     const uint64_t xh = umma_desc(xbase + 0 * G5_TILE_BYTES + koff, lbo, sbo);
                     const uint64_t xm = umma_desc(xbase + 1 * G5_TILE_BYTES + koff, lbo, sbo);
-                    const uint64_t xl = umma_desc(xbase + 2 * G5_TILE_BYTES + koff, lbo, sbo);
                     // smallest terms first
-                    umma_bf16(tmem_d, wlo, xm, idesc, (it | ks) != 0);
-                    umma_bf16(tmem_d, whi, xl, idesc, 1);
-                    umma_bf16(tmem_d, wlo, xh, idesc, 1);
-                    umma_bf16(tmem_d, whi, xm, idesc, 1);
-                    umma_bf16(tmem_d, whi, xh, idesc, 1);
+                    umma_f16(tmem_d, wlo, xh, idesc, (it | ks) != 0);
+                    umma_f16(tmem_d, whi, xm, idesc, 1);
+                    umma_f16(tmem_d, whi, xh, idesc, 1);
                 }
                 umma_commit(&done_bar[s]);
             }
@@ -197,44 +200,43 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
         const int gn = f0 + drow;
         // this thread's Q4 block of the first k-step (rows beyond N: nibble 8 = weight 0, scale 0)
         uint4 q_cur = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
-        float d_cur = 0.0f;
+        __half d_cur = __float2half(0.0f);
         if (gn < a.N && kc_begin < kc_end) {
             const size_t blk = (size_t)gn * bpr + (size_t)kc_begin * 2 + dblk;
             q_cur = __ldg(a.qs + blk);
-            d_cur = __half2float(__ldg(a.ds + blk));
+            d_cur = __ldg(a.ds + blk);
         }
+        const __half2 c1032 = __half2half2(__ushort_as_half((unsigned short)0x6408));  // 1032 = 1024 + 8
+        const __half2 wsc = __float2half2_rn(G5_WSCALE);
         for (int kc = kc_begin; kc < kc_end; ++kc) {
             const int it = kc - kc_begin;
             const int s = it & 1, use = it >> 1;
             unsigned char *stage = smem + (size_t)s * G5_WSTAGE_BYTES;
             const uint4 q = q_cur;
-            const float dd = d_cur;
+            const __half2 d2 = __hmul2(__half2half2(d_cur), wsc);  // d * 2^8, exact
             if (gn < a.N && kc + 1 < kc_end) {  // next k-step's block: its L2 latency hides behind this step
                 const size_t blk = (size_t)gn * bpr + (size_t)(kc + 1) * 2 + dblk;
                 q_cur = __ldg(a.qs + blk);
-                d_cur = __half2float(__ldg(a.ds + blk));
+                d_cur = __ldg(a.ds + blk);
             }
-            // 16 weights of the block: low nibbles (elements 0..15, dhalf = 0) or high nibbles (16..31), times d.
-            // nibble n -> float (n - 8) without an int->float conversion: 0x4B000000 | n = 2^23 + n
+            // 16 weights of the block: low nibbles (elements 0..15, dhalf = 0) or high nibbles (16..31).  All in half2 on the
+            // FMA pipe: nibble n -> half(1024 + n) by OR-ing 0x6400 (ulp = 1 there) -> n - 8 = h - 1032 (exact) ->
+            // hi = RN(n8 * d') (HMUL2), lo = n8 * d' - hi (HFMA2; the residual of an f16 product is representable)
             const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-            float wv[16];
-#pragma unroll
-            for (int wi = 0; wi < 4; ++wi)
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const uint32_t n = (w4[wi] >> (8 * t + 4 * dhalf)) & 0xFu;
-                    wv[wi * 4 + t] = (__uint_as_float(0x4B000000u | n) - 8388616.0f) * dd;
-                }
             uint32_t ph[8], pl[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float v0 = wv[2 * e], v1 = wv[2 * e + 1];
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);  // one packed conversion per pair
-                const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2);
-                const float r0 = v0 - __uint_as_float(hb << 16), r1 = v1 - __uint_as_float(hb & 0xFFFF0000u);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
-                ph[e] = hb;
-                pl[e] = *reinterpret_cast<const uint32_t *>(&l2);
+            for (int wi = 0; wi < 4; ++wi) {
+                const uint32_t nib = (dhalf ? (w4[wi] >> 4) : w4[wi]) & 0x0F0F0F0Fu;   // bytes = elements 4wi .. 4wi+3
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                    uint32_t hb;   // {0x6400 | n_(2pr), 0x6400 | n_(2pr+1)}
+                    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(hb) : "r"(nib), "r"(0x64646464u), "r"(pr ? 0x4342u : 0x4140u));
+                    const __half2 n8 = __hsub2(*reinterpret_cast<const __half2 *>(&hb), c1032);
+                    const __half2 hi = __hmul2(n8, d2);
+                    const __half2 lo = __hfma2(n8, d2, __hneg2(hi));
+                    ph[wi * 2 + pr] = *reinterpret_cast<const uint32_t *>(&hi);
+                    pl[wi * 2 + pr] = *reinterpret_cast<const uint32_t *>(&lo);
+                }
             }
             if (it >= G5_STAGES) {
                 mbar_wait(&done_bar[s], (uint32_t)((use - 1) & 1));  // MMAs that read this W stage have retired
@@ -315,10 +317,11 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
         }
         if (run_epilogue && ew) {
             const float bsv = (a.bias && feat < a.N) ? a.bias[feat] : 0.0f;
+            const float my_sc = a.oscale[tok0 + col0 + lane];   // token column col0 + lane; broadcast per column below
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int tok = tok0 + col0 + j;
-                float v = __uint_as_float(r[j]);
+                float v = __uint_as_float(r[j]) * __shfl_sync(0xffffffffu, my_sc, j);
                 if (EPI == EPI_SILU_MUL) {
                     // features (2i, 2i+1) = (gate, up) sit in adjacent lanes
                     const float other = __shfl_xor_sync(0xffffffffu, v, 1);
@@ -340,37 +343,60 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
     }
 }
 
-// X (f32, row-major [M][K]) -> three bf16 pieces in the UMMA tile layout, optionally through RMSNorm
-// (x / sqrt(mean(x^2)+eps) * gamma (* ada)).  CTA = 8 token rows; rows >= M are written as zeros.
+// X (f32, row-major [M][K]) -> two f16 pieces of X * 2^s_t in the UMMA tile layout, optionally through RMSNorm
+// (x / sqrt(mean(x^2)+eps) * gamma (* ada)); s_t = per-token power of two putting the row maximum in [2^7, 2^8);
+// oscale[t] = 2^-(s_t + 8) undoes it (and the weights' 2^8) in the GEMM epilogue.  CTA = 8 token rows; rows >= M are
+// written as zeros.
 __global__ void __launch_bounds__(256) split_tiles_kernel(const float *__restrict__ x, int M, int K, const float *__restrict__ gamma,
-                                                          const float *__restrict__ ada, float eps,
-                                                          __nv_bfloat16 *__restrict__ xt, int TT, int KC) {
-    __shared__ float ssq_part[32][8];
-    __shared__ float rms_s[8];
+                                                          const float *__restrict__ ada, float eps, __half *__restrict__ xt,
+                                                          float *__restrict__ oscale, int TT, int KC) {
+    __shared__ float ssq_part[32][8], max_part[32][8];
+    __shared__ float rms_s[8], sc_s[8];
     const int r8 = threadIdx.x & 7, cth = threadIdx.x >> 3;  // cth: 0..31 strides over the 16-byte chunks
     const int row = blockIdx.x * 8 + r8;
     const int nchunk = K >> 3;
     const bool valid = row < M;
     const float *xr = x + (size_t)(valid ? row : 0) * K;
-    if (gamma) {
-        float ssq = 0.0f;
+    {   // pass 1: sum of squares (RMSNorm) and max |x * gamma * ada| (the row maximum after the norm is this / rms)
+        float ssq = 0.0f, mx = 0.0f;
         if (valid)
             for (int c = cth; c < nchunk; c += 32) {
                 const float4 v0 = *reinterpret_cast<const float4 *>(xr + c * 8);
                 const float4 v1 = *reinterpret_cast<const float4 *>(xr + c * 8 + 4);
-                ssq = fmaf(v0.x, v0.x, ssq); ssq = fmaf(v0.y, v0.y, ssq); ssq = fmaf(v0.z, v0.z, ssq); ssq = fmaf(v0.w, v0.w, ssq);
-                ssq = fmaf(v1.x, v1.x, ssq); ssq = fmaf(v1.y, v1.y, ssq); ssq = fmaf(v1.z, v1.z, ssq); ssq = fmaf(v1.w, v1.w, ssq);
+                float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    ssq = fmaf(v[e], v[e], ssq);
+                    float g = v[e];
+                    if (gamma) {
+                        g *= gamma[c * 8 + e];
+                        if (ada) g *= ada[c * 8 + e];
+                    }
+                    mx = fmaxf(mx, fabsf(g));
+                }
             }
         ssq_part[cth][r8] = ssq;
+        max_part[cth][r8] = mx;
         __syncthreads();
         if (threadIdx.x < 8) {
-            float s = 0.0f;
-            for (int i = 0; i < 32; ++i) s += ssq_part[i][threadIdx.x];
-            rms_s[threadIdx.x] = sqrtf(s / (float)K + eps);
+            float s = 0.0f, m = 0.0f;
+            for (int i = 0; i < 32; ++i) {
+                s += ssq_part[i][threadIdx.x];
+                m = fmaxf(m, max_part[i][threadIdx.x]);
+            }
+            const float rms = gamma ? sqrtf(s / (float)K + eps) : 1.0f;
+            rms_s[threadIdx.x] = rms;
+            m = m / rms * 1.0001f;  // the split below rounds (v / rms) * gamma slightly differently: stay below 2^8
+            int e = (int)((__float_as_uint(m) >> 23) & 0xFF) - 127;
+            if (!(m > 0.0f) || m > 3.0e38f) e = 7;   // all-zero (or non-finite) row: scale 1
+            e = e < -100 ? -100 : (e > 100 ? 100 : e);
+            sc_s[threadIdx.x] = __uint_as_float((uint32_t)(7 - e + 127) << 23);            // 2^(7 - e)
+            const int grow = blockIdx.x * 8 + threadIdx.x;
+            oscale[grow] = __uint_as_float((uint32_t)(e - 7 - 8 + 127) << 23);              // 2^(e - 7) / 2^8
         }
         __syncthreads();
     }
-    const float rms = gamma ? rms_s[r8] : 1.0f;
+    const float rms = rms_s[r8], sc = sc_s[r8];
     const int tt = row / G5_BN, rin = row % G5_BN;
     const size_t piece = (size_t)TT * KC * (G5_TILE_BYTES / 2);
     for (int c = cth; c < nchunk; c += 32) {
@@ -387,28 +413,20 @@ __global__ void __launch_bounds__(256) split_tiles_kernel(const float *__restric
                 }
             }
         }
-        uint32_t p[3][4];
+        uint32_t p[2][4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            uint32_t w[3] = {0, 0, 0};
-#pragma unroll
-            for (int hlf = 0; hlf < 2; ++hlf) {
-                const float f = v[2 * e + hlf];
-                const __nv_bfloat16 bh = __float2bfloat16_rn(f);
-                const float r1 = f - __bfloat162float(bh);
-                const __nv_bfloat16 bm = __float2bfloat16_rn(r1);
-                const float r2 = r1 - __bfloat162float(bm);
-                const __nv_bfloat16 bl = __float2bfloat16_rn(r2);
-                w[0] |= (uint32_t)__bfloat16_as_ushort(bh) << (16 * hlf);
-                w[1] |= (uint32_t)__bfloat16_as_ushort(bm) << (16 * hlf);
-                w[2] |= (uint32_t)__bfloat16_as_ushort(bl) << (16 * hlf);
-            }
-            p[0][e] = w[0]; p[1][e] = w[1]; p[2][e] = w[2];
+            const float f0 = v[2 * e] * sc, f1 = v[2 * e + 1] * sc;   // power-of-two scale: exact
+            const __half2 h = __floats2half2_rn(f0, f1);
+            const float2 hf = __half22float2(h);
+            const __half2 m = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+            p[0][e] = *reinterpret_cast<const uint32_t *>(&h);
+            p[1][e] = *reinterpret_cast<const uint32_t *>(&m);
         }
         // tile (tt, kc = c/8), chunk-in-tile c%8, row rin: [8][128][16 B]
         const size_t off = ((size_t)tt * KC + (c >> 3)) * (G5_TILE_BYTES / 2) + (size_t)((c & 7) * G5_BN + rin) * 8;
 #pragma unroll
-        for (int s = 0; s < 3; ++s)
+        for (int s = 0; s < G5_XPIECES; ++s)
             *reinterpret_cast<uint4 *>(xt + s * piece + off) = make_uint4(p[s][0], p[s][1], p[s][2], p[s][3]);
     }
 }
@@ -417,17 +435,27 @@ __global__ void __launch_bounds__(256) split_tiles_kernel(const float *__restric
 
 bool gemm_tc5_supported(const Q4Weight &w, int M) { return w.N % G5_BM == 0 && w.K % G5_BK == 0 && M >= 1; }
 
+// f16 elements of the split buffer: two pieces of tiles + the per-token output scales (floats) behind them
+static size_t g5_tiles_elems(int M, int K) {
+    const size_t TT = (size_t)(M + G5_BN - 1) / G5_BN;
+    return G5_XPIECES * TT * (size_t)(K / G5_BK) * (G5_TILE_BYTES / 2);
+}
 size_t gemm_tc5_split_elems(int M, int K) {
     const size_t TT = (size_t)(M + G5_BN - 1) / G5_BN;
-    return 3 * TT * (size_t)(K / G5_BK) * (G5_TILE_BYTES / 2);
+    return g5_tiles_elems(M, K) + 2 * TT * G5_BN + 8;
+}
+static float *g5_oscale_ptr(void *xt, int M, int K) {
+    size_t off = g5_tiles_elems(M, K) * 2;          // bytes
+    off = (off + 15) & ~(size_t)15;
+    return reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(xt) + off);
 }
 
-// x [M][K] f32 -> xt (bf16 pieces, tile layout); rows padded to a multiple of 128 with zeros
+// x [M][K] f32 -> xt (f16 pieces, tile layout; per-token scales behind them); rows padded to a multiple of 128 with zeros
 void launch_split_tiles(const float *x, int M, int K, const float *gamma, const float *ada, float eps, void *xt,
                         cudaStream_t st) {
     VOX_CHECK(K % G5_BK == 0, VOX_EINVAL, "split_tiles: K=%d not a multiple of 64", K);
     const int TT = (M + G5_BN - 1) / G5_BN, KC = K / G5_BK;
-    split_tiles_kernel<<<TT * (G5_BN / 8), 256, 0, st>>>(x, M, K, gamma, ada, eps, (__nv_bfloat16 *)xt, TT, KC);
+    split_tiles_kernel<<<TT * (G5_BN / 8), 256, 0, st>>>(x, M, K, gamma, ada, eps, (__half *)xt, g5_oscale_ptr(xt, M, K), TT, KC);
     tc_count_launch("split_tiles");
 }
 
@@ -440,7 +468,8 @@ void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int 
     a.N = w.N;
     a.K = w.K;
     a.M = M;
-    a.xt = (const __nv_bfloat16 *)xt;
+    a.xt = (const __half *)xt;
+    a.oscale = g5_oscale_ptr(const_cast<void *>(xt), M, w.K);
     a.TT = (M + G5_BN - 1) / G5_BN;
     a.KC = w.K / G5_BK;
     a.y = y;

@@ -964,6 +964,7 @@ mel_kernel(const float *__restrict__ samples, size_t n, size_t sample_stride, co
            const float *__restrict__ fb_vals, const int *__restrict__ fb_start, const int *__restrict__ fb_len,
            int fb_stride, float *__restrict__ out, int frames, int layout, int frame0) {
     __shared__ float ws[MEL_FR][MEL_NFFT];
+    __shared__ __align__(16) float sp[(MEL_FR - 1) * MEL_HOP + MEL_NFFT];
     __shared__ float ct[MEL_NFFT], stt[MEL_NFFT];
     __shared__ float pw[MEL_FR][MEL_NFREQ + 3];
     const int b = blockIdx.y;
@@ -976,16 +977,30 @@ mel_kernel(const float *__restrict__ samples, size_t n, size_t sample_stride, co
         ct[i] = c;
         stt[i] = s;
     }
+    // the CTA's 8 frames read one contiguous span of the signal ([160 f0 - 200, 160 (f0 + 7) + 200) = 1520 samples):
+    // stage it ONCE in shared memory -- 128-bit loads where the span lies inside the signal, reflected indices
+    // (torch.stft center=True, mel.rs:190-205) only at the two ends -- then window the frames out of shared memory
+    {
+        const long long span0 = (long long)f0 * MEL_HOP - MEL_NFFT / 2;
+        constexpr int SPAN = (MEL_FR - 1) * MEL_HOP + MEL_NFFT;   // 1520
+        static_assert(SPAN % 4 == 0, "span is float4-sized");
+        const bool interior = span0 >= 0 && span0 + SPAN <= nn && ((reinterpret_cast<uintptr_t>(sig + span0) & 15) == 0);
+        if (interior) {
+            const float4 *src4 = reinterpret_cast<const float4 *>(sig + span0);
+            for (int i = threadIdx.x; i < SPAN / 4; i += MEL_THREADS) reinterpret_cast<float4 *>(sp)[i] = src4[i];
+        } else {
+            for (int i = threadIdx.x; i < SPAN; i += MEL_THREADS) {
+                long long src = span0 + i;
+                if (src < 0) { src = -src; if (src > nn - 1) src = nn > 0 ? nn - 1 : 0; }
+                else if (src >= nn) { src = 2 * nn - 2 - src; if (src < 0) src = 0; }
+                sp[i] = nn > 0 ? sig[src] : 0.0f;
+            }
+        }
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < MEL_FR * MEL_NFFT; i += MEL_THREADS) {
         const int f = i / MEL_NFFT, j = i - f * MEL_NFFT;
-        float v = 0.0f;
-        if (f0 + f < frames) {
-            long long src = (long long)(f0 + f) * MEL_HOP + j - MEL_NFFT / 2;  // index into unpadded signal
-            if (src < 0) { src = -src; if (src > nn - 1) src = nn > 0 ? nn - 1 : 0; }
-            else if (src >= nn) { src = 2 * nn - 2 - src; if (src < 0) src = 0; }
-            v = (nn > 0 ? sig[src] : 0.0f) * window[j];
-        }
-        ws[f][j] = v;
+        ws[f][j] = (f0 + f < frames) ? sp[f * MEL_HOP + j] * window[j] : 0.0f;
     }
     __syncthreads();
     if (threadIdx.x < MEL_NFREQ) {
@@ -1035,38 +1050,63 @@ void launch_mel(const float *samples, int B, size_t n, size_t sample_stride, con
     post_launch("mel");
 }
 
-// peak_normalize (io.rs:59-68) + pad_audio (pad.rs:89-103) on device
-__global__ void peak_scale_kernel(const float *__restrict__ in, size_t n, float target, int do_norm,
-                                  float *__restrict__ scale_out) {
-    __shared__ float red[32];
-    const float *s = in + (size_t)blockIdx.x * n;
+// peak_normalize (io.rs:59-68) + pad_audio (pad.rs:89-103) on device.
+// max|x| per stream: PK_BLOCKS CTAs per stream, float4 loads, one atomicMax per CTA on the float's bit pattern (|x| >= 0:
+// unsigned order == float order, so the result is exact and independent of the arrival order).  The scale
+// (target / max, or 1 when max < 1e-10: io.rs:61-63) is derived by the consumer, which also writes the padded copy.
+constexpr int PK_BLOCKS = 64, PK_THREADS = 256;
+__global__ void __launch_bounds__(PK_THREADS) peak_max_kernel(const float *__restrict__ in, size_t n, unsigned *__restrict__ max_bits) {
+    __shared__ float red[PK_THREADS / 32];
+    const float *s = in + (size_t)blockIdx.y * n;
     float mx = 0.0f;
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, fabsf(s[i]));
+    const size_t stride = (size_t)gridDim.x * PK_THREADS;
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(s) & 15) == 0)) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(s);
+        for (size_t i = (size_t)blockIdx.x * PK_THREADS + threadIdx.x; i < n / 4; i += stride) {
+            const float4 v = s4[i];
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * PK_THREADS + threadIdx.x; i < n; i += stride) mx = fmaxf(mx, fabsf(s[i]));
+    }
     mx = warp_max(mx);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
     __syncthreads();
     if (threadIdx.x < 32) {
-        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+        float v = threadIdx.x < PK_THREADS / 32 ? red[threadIdx.x] : 0.0f;
         v = warp_max(v);
-        if (threadIdx.x == 0) scale_out[blockIdx.x] = (!do_norm || v < 1e-10f) ? 1.0f : target / v;
+        if (threadIdx.x == 0) atomicMax(max_bits + blockIdx.y, __float_as_uint(v));
     }
 }
-__global__ void scale_pad_kernel(const float *__restrict__ in, size_t n, const float *__restrict__ scale,
-                                 int do_norm, float *__restrict__ out, size_t out_stride, size_t left) {
+__global__ void scale_pad_kernel(const float *__restrict__ in, size_t n, const float *__restrict__ max_abs, float target,
+                                 int do_norm, float *__restrict__ out, size_t out_stride, size_t left, int vec4) {
     const int b = blockIdx.y;
+    const float mx = max_abs[b];
+    const float scale = (!do_norm || mx < 1e-10f) ? 1.0f : target / mx;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float v = in[(size_t)b * n + i];
-    out[(size_t)b * out_stride + left + i] = do_norm ? v * scale[b] : v;
+    if (vec4) {
+        if (i >= n / 4) return;
+        float4 v = reinterpret_cast<const float4 *>(in + (size_t)b * n)[i];
+        if (do_norm) { v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; }
+        reinterpret_cast<float4 *>(out + (size_t)b * out_stride + left)[i] = v;
+    } else {
+        if (i >= n) return;
+        const float v = in[(size_t)b * n + i];
+        out[(size_t)b * out_stride + left + i] = do_norm ? v * scale : v;
+    }
 }
 
 void launch_peak_normalize_pad(const float *in, int B, size_t n, float target, int do_norm, float *out,
                                size_t out_stride, size_t left, float *scale_buf, cudaStream_t st) {
     cudaMemsetAsync(out, 0, sizeof(float) * out_stride * B, st);
-    peak_scale_kernel<<<B, 1024, 0, st>>>(in, n, target, do_norm, scale_buf);
-    post_launch("peak_scale");
-    dim3 grid((unsigned)((n + 255) / 256), B);
-    scale_pad_kernel<<<grid, 256, 0, st>>>(in, n, scale_buf, do_norm, out, out_stride, left);
+    cudaMemsetAsync(scale_buf, 0, sizeof(float) * B, st);
+    peak_max_kernel<<<dim3(PK_BLOCKS, B), PK_THREADS, 0, st>>>(in, n, reinterpret_cast<unsigned *>(scale_buf));
+    post_launch("peak_max");
+    const int vec4 = (n % 4 == 0 && left % 4 == 0 && out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+    const size_t work = vec4 ? n / 4 : n;
+    dim3 grid((unsigned)((work + 255) / 256), B);
+    scale_pad_kernel<<<grid, 256, 0, st>>>(in, n, scale_buf, target, do_norm, out, out_stride, left, vec4);
     post_launch("scale_pad");
 }
 
