@@ -241,6 +241,11 @@ int32_t vox_stream_tick(vox_stream_pool *p, vox_stream_stats *stats /* nullable 
 int32_t vox_stream_poll_ids(vox_stream_pool *p, int32_t session, int32_t *ids, size_t cap, size_t *n, int32_t *done);
 /* parity/debug: audio embeddings produced so far, [n][dec_dim] host */
 int32_t vox_stream_audio_embeds(vox_stream_pool *p, int32_t session, float *out, size_t cap_floats, int32_t *n);
+/* encode_audio_with_cache (model.rs:790-799) with upstream's semantics: one mel chunk [128][t_frames] (host) through the
+ * conv stem on its own, the encoder layers over the session's K/V caches (RoPE / mask offsets = cached length), x4 stack
+ * and adapter -> the chunk's S/4 embeddings [n][dec_dim] (host).  Chunk-wise alternative to push_pcm/tick; do not mix. */
+int32_t vox_stream_encode_chunk(vox_stream_pool *p, int32_t session, const float *mel, int32_t t_frames, float *audio_embeds,
+                                size_t cap_floats, int32_t *n);
 int32_t vox_stream_close(vox_stream_pool *p, int32_t session);
 void vox_stream_pool_free(vox_stream_pool *p);
 

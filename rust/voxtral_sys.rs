@@ -88,6 +88,8 @@ extern "C" {
     pub fn vox_stream_finish(p: *mut vox_stream_pool, session: i32) -> i32;
     pub fn vox_stream_tick(p: *mut vox_stream_pool, stats: *mut vox_stream_stats) -> i32;
     pub fn vox_stream_poll_ids(p: *mut vox_stream_pool, session: i32, ids: *mut i32, cap: usize, n: *mut usize, done: *mut i32) -> i32;
+    pub fn vox_stream_encode_chunk(p: *mut vox_stream_pool, session: i32, mel: *const f32, t_frames: i32, audio_embeds: *mut f32,
+                                   cap: usize, n: *mut i32) -> i32;
     pub fn vox_stream_close(p: *mut vox_stream_pool, session: i32) -> i32;
     pub fn vox_stream_pool_free(p: *mut vox_stream_pool);
     // src/tokenizer/mod.rs

@@ -185,3 +185,42 @@ def test_full_size_batch_invariance_and_determinism(vx, full_model):
     finally:
         full_model.debug("graph_on")
     assert len({tuple(r) for r in a.tolist()}) == 8            # different audio -> different ids
+
+
+@pytest.mark.slow
+def test_full_size_streaming_sessions_equal_golden(vx, full_model):
+    """vox_stream_* on the full-size model: two live sessions (the two golden utterances, the second one opened 1.2 s
+    later) fed 80 ms per tick -> the ids of the whole-utterance goldens; most tokens are out before the audio ends."""
+    golds = [np.load(os.path.join(HERE, "golden", n)) for n in ("full_s42_16s.npz", "full_s42_16s_b.npz")]
+    audios = [vx.peak_normalize(synth.speechlike(16.0, seed=1234)), vx.peak_normalize(synth.speechlike(16.0, seed=99))]
+    pool = vx.StreamingPool(full_model, max_sessions=2, max_seconds=20.0)
+    try:
+        sids, fed, got, before_end = [None, None], [0, 0], [[], []], [0, 0]
+        for tick in range(260):
+            for i in range(2):
+                if tick == 15 * i:
+                    sids[i] = pool.open()
+                if sids[i] is not None and fed[i] < audios[i].size:
+                    pool.push(sids[i], audios[i][fed[i]:fed[i] + 1280])
+                    fed[i] += 1280
+                    if fed[i] >= audios[i].size:
+                        before_end[i] = -1      # mark: count after this tick
+            pool.tick()
+            for i in range(2):
+                if sids[i] is not None:
+                    got[i] += pool.poll(sids[i])[0]
+                    if before_end[i] == -1:
+                        before_end[i] = len(got[i])
+            if all(f >= a.size for f, a in zip(fed, audios)):
+                break
+        for i in range(2):
+            pool.finish(sids[i])
+        pool.tick()
+        for i in range(2):
+            ids, done = pool.poll(sids[i])
+            got[i] += ids
+            assert done
+            assert assert_ids_match(np.array(got[i], np.int32), golds[i], f"full/16s streamed session {i}", full_model, audio=audios[i]) >= 108 - 3
+            assert 80 <= before_end[i] < 108
+    finally:
+        pool.close()

@@ -116,3 +116,24 @@ def test_pool_capacity_and_errors(vx, tiny_model):
     sid2 = pool.open()
     assert sid2 == sid
     pool.close()
+
+
+def test_encode_audio_with_cache_matches_upstream_semantics(vx, tiny_model, tiny_oracle):
+    """vox_stream_encode_chunk == the oracle's encode_audio_with_cache (model.rs:790-799: chunk-local conv stem, encoder
+    K/V caches with RoPE / mask offsets): two chunks, the second one's queries reaching back over a window (20) that is
+    smaller than the cached length; and a single chunk == the uncached encode_audio."""
+    import torch
+    mel = omel.mel_tensor_from_audio(omel.peak_normalize(omel.speechlike(4.0, 6)))
+    pool = vx.StreamingPool(tiny_model, max_sessions=2, max_seconds=8.0)
+    sid = pool.open()
+    cache = tiny_oracle.new_encoder_cache()
+    for a, b in ((0, 160), (160, 480), (480, mel.shape[2])):
+        exp = tiny_oracle.encode_audio_with_cache(mel[:, :, a:b], cache).numpy()
+        got = pool.encode_audio_with_cache(sid, mel[0, :, a:b])
+        assert got.shape == exp.shape and np.abs(got - exp).max() < 1e-3, (a, b, np.abs(got - exp).max())
+    sid2 = pool.open()
+    whole = pool.encode_audio_with_cache(sid2, mel[0])
+    assert np.abs(whole - tiny_model.encode_audio(mel)[0]).max() < 1e-4
+    with pytest.raises(vx.VoxtralError, match="do not mix"):
+        pool.push(sid2, np.zeros(1280, np.float32)); pool.tick(); pool.encode_audio_with_cache(sid2, mel[0, :, :64])
+    pool.close()

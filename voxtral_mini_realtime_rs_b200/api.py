@@ -141,6 +141,7 @@ _SIGS = {
     "vox_stream_tick": (C.c_int32, [_P, _P]),
     "vox_stream_poll_ids": (C.c_int32, [_P, C.c_int32, _P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]),
     "vox_stream_audio_embeds": (C.c_int32, [_P, C.c_int32, _P, C.c_size_t, C.POINTER(C.c_int32)]),
+    "vox_stream_encode_chunk": (C.c_int32, [_P, C.c_int32, _P, C.c_int32, _P, C.c_size_t, C.POINTER(C.c_int32)]),
     "vox_stream_close": (C.c_int32, [_P, C.c_int32]),
     "vox_stream_pool_free": (None, [_P]),
     "vox_tokenizer_from_file": (C.c_int32, [C.c_char_p, C.POINTER(_P)]),
@@ -710,6 +711,20 @@ class StreamingPool:
         out = np.empty((n.value, self.dec_dim), np.float32)
         _check(lib().vox_stream_audio_embeds(self._p, session, _ptr(out), out.size, C.byref(n)))
         return out
+
+    def encode_audio_with_cache(self, session: int, mel) -> np.ndarray:
+        """mel chunk [128,T] (or [1,128,T]) -> the chunk's audio embeddings [T/16, dec_dim]; the session's encoder
+        K/V caches are extended (Q4VoxtralModel::encode_audio_with_cache, model.rs:790-799)."""
+        mel = _f32(mel)
+        if mel.ndim == 3:
+            mel = mel[0]
+        t = mel.shape[1]
+        t1 = (t + 2 - 3) // 2 + 1
+        s = (t1 + 2 - 3) // 2 + 1
+        out = np.empty((s // 4 + 1, self.dec_dim), np.float32)
+        n = C.c_int32()
+        _check(lib().vox_stream_encode_chunk(self._p, session, _ptr(mel), t, _ptr(out), out.size, C.byref(n)))
+        return out[:n.value].copy()
 
     def close_session(self, session: int):
         _check(lib().vox_stream_close(self._p, session))

@@ -953,6 +953,12 @@ int32_t vox_stream_audio_embeds(vox_stream_pool *p, int32_t session, float *out,
     }
     VOX_API_END
 }
+int32_t vox_stream_encode_chunk(vox_stream_pool *p, int32_t session, const float *mel, int32_t t, float *out, size_t cap, int32_t *n) {
+    VOX_API_BEGIN
+    REQUIRE(p); REQUIRE(mel); REQUIRE(out); REQUIRE(n);
+    *n = p->p->encode_chunk(session, mel, t, out, cap);
+    VOX_API_END
+}
 int32_t vox_stream_close(vox_stream_pool *p, int32_t session) {
     VOX_API_BEGIN
     REQUIRE(p);

@@ -96,7 +96,8 @@ struct MegaParams {
     // optional warp-level trace of CTA 0's first 6 tile groups of the lm_head phase: [16 warps][6 groups][8 stamps]
     unsigned long long *trace_w = nullptr;
     // experiment switches (VOX_MEGA_FLAGS): 1 no evict-first hint, 2 no KV-cache L2 prefetch, 4 no norm-weight prefetch,
-    // 8 fragments copied in one piece (no per-CTA rotation)
+    // 8 fragments copied in one piece (no per-CTA rotation), 16 weight loop without the arithmetic (garbage results:
+    // measures the memory pipeline alone)
     int flags = 0;
 };
 

@@ -3,13 +3,14 @@
 // Reference arithmetic: src/gguf/shader_naive.wgsl:31-98 (w = (q-8)*d in f32, f32 accumulate).
 //
 // f32-grade accuracy on f16 tensor cores ("2 x 2 split, 3 products"): tcgen05 has no f32-input MMA, so
-//   w * 2^8  = w_hi + w_lo     f16 pieces, exact: (q-8)*d has <= 14 significant bits; hi = RN_f16((q-8)*d'), lo = the exact
-//                              residual of that rounding -- both produced by two half2 FMA-pipe instructions per weight pair
-//                              (HMUL2, HFMA2), no float conversions (d' = d * 2^8 keeps lo out of the subnormal range)
+//   w * 2^8  = w_hi + w_lo     f16 pieces, exact: (q-8)*d has <= 14 significant bits; hi = the 11-bit Veltkamp head of the f32
+//                              product, lo = the exact tail; their f16 bit patterns are assembled with shifts and masks
+//                              (g5_pack_f16x2) -- no half2 arithmetic and no conversion instructions, which run on the
+//                              quarter-rate XU pipe on this part (d' = d * 2^8 keeps lo out of the subnormal range)
 //   x * 2^s_t = x_h + x_m      f16 pieces, 22 bits; s_t = per-token power of two that puts the row maximum in [2^7, 2^8)
 // and the product is accumulated in f32 TMEM from the three largest terms
 //   w_hi x_h + w_hi x_m + w_lo x_h            (dropped: w_lo x_m ~ 2^-22 |w||x|, the f32 rounding level)
-// i.e. 3 kind::f16 MMAs per 16-wide K step (round 1 used bf16 pieces: 3 x 2 pieces, 5 MMAs, and ~3x the dequant ALU work).
+// i.e. 3 kind::f16 MMAs per 16-wide K step (round 1 used bf16 pieces: 3 x 2 pieces, 5 MMAs, F2FP conversions on the XU pipe).
 // The epilogue multiplies token column t by 2^-(s_t + 8).  Measured against the oracle in tests/.
 //
 // "Swap-AB" tiling: the UMMA M dimension (128 TMEM lanes) runs over output features, the UMMA N
@@ -22,6 +23,7 @@
 //   * one thread issues the tcgen05.mma's; tcgen05.commit -> mbarrier frees the stage (2 stages);
 //   * epilogue: tcgen05.ld 32 lanes x 32 columns per warp; lane = feature, so every column is a
 //     coalesced 128-byte store of Y[token][f0+32q .. +31]; bias / residual / GELU / SiLU*up fused.
+#include <algorithm>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -38,17 +40,20 @@ constexpr int G5_DQ_WARPS = 16;                           // dequantising warps 
 constexpr int G5_DQ_THREADS = G5_DQ_WARPS * 32;
 constexpr int G5_THREADS = G5_DQ_THREADS + 32;            // + the control warp (TMA + MMA issue)
 constexpr int G5_BM = 128;   // features per CTA (UMMA M)
-constexpr int G5_BN = 128;   // tokens per CTA (UMMA N)
+constexpr int G5_BN = 128;   // tokens per CTA (UMMA N) for small problems; 256 when M >= G5_WIDE_M (halves the dequant work and
+                             // the A-operand shared-memory reads per output: the 128x128 tile is smem-bandwidth bound)
+constexpr int G5_WIDE_M = 512;
+__host__ __device__ constexpr int g5_bn(int M) { return M >= G5_WIDE_M ? 256 : 128; }
 constexpr int G5_BK = 64;    // K per pipeline stage
 constexpr int G5_TILE_BYTES = G5_BM * G5_BK * 2;          // 16 KB: one bf16 operand tile
 constexpr int G5_STAGES = 2;                              // weight stages (w_hi, w_lo), dequantised in-kernel
 constexpr int G5_XSTAGES = 3;                             // activation stages (x_h, x_m), fetched one k-step ahead
 constexpr int G5_WSTAGE_BYTES = 2 * G5_TILE_BYTES;
 constexpr int G5_XPIECES = 2;
-constexpr int G5_XSTAGE_BYTES = G5_XPIECES * G5_TILE_BYTES;
+__host__ __device__ constexpr int g5_xtile_bytes(int BN) { return BN * G5_BK * 2; }
+__host__ __device__ constexpr int g5_xstages(int BN) { return BN == 256 ? 2 : 3; }
 constexpr float G5_WSCALE = 256.0f;                       // weights enter the MMA times 2^8 (see header)
-constexpr int G5_SMEM_BYTES = G5_STAGES * G5_WSTAGE_BYTES + G5_XSTAGES * G5_XSTAGE_BYTES;  // 208 KB
-constexpr int G5_TMEM_COLS = 128;
+__host__ __device__ constexpr int g5_smem_bytes(int BN) { return G5_STAGES * G5_WSTAGE_BYTES + g5_xstages(BN) * G5_XPIECES * g5_xtile_bytes(BN); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -106,6 +111,16 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// f16x2 bit pattern of two floats v0', v1' that are (value * 2^-112) of numbers exactly representable in f16 -- normal,
+// subnormal or zero: with the exponent re-biased by the 2^-112 factor, the f16 exponent/mantissa field of v is simply bits
+// 13..27 of v' (an f32 denormal v' lands on the matching f16 denormal), so no conversion instruction (XU pipe) is needed.
+__device__ __forceinline__ uint32_t g5_pack_f16x2(const float v0, const float v1) {
+    const uint32_t b0 = __float_as_uint(v0), b1 = __float_as_uint(v1);
+    const uint32_t em = ((b0 >> 13) & 0x00007FFFu) | ((b1 << 3) & 0x7FFF0000u);
+    const uint32_t sg = ((b0 >> 16) & 0x00008000u) | (b1 & 0x80000000u);
+    return em | sg;
+}
+
 struct G5Args {
     const uint4 *qs;      // row-major Q4 planes (kernels.h Q4Weight)
     const __half *ds;
@@ -123,17 +138,18 @@ struct G5Args {
     int *counters;
 };
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a) {
+    constexpr int XSTAGES = g5_xstages(BN), XTILE = g5_xtile_bytes(BN), XSTAGE_BYTES = G5_XPIECES * XTILE, TMEM_COLS = BN;
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full_bar[G5_XSTAGES], wfull_bar[G5_STAGES], done_bar[G5_STAGES];
+    __shared__ __align__(8) uint64_t full_bar[XSTAGES], wfull_bar[G5_STAGES], done_bar[G5_STAGES];
     __shared__ uint32_t tmem_base_smem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int f0 = blockIdx.x * G5_BM, tt = blockIdx.y, tok0 = tt * G5_BN;
+    const int f0 = blockIdx.x * G5_BM, tt = blockIdx.y, tok0 = tt * BN;
     const int bpr = a.K >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < G5_XSTAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < XSTAGES; ++s) mbar_init(&full_bar[s], 1);
         for (int s = 0; s < G5_STAGES; ++s) {
             mbar_init(&wfull_bar[s], G5_DQ_WARPS);  // one arrival per dequantising warp
             mbar_init(&done_bar[s], 1);
@@ -142,7 +158,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)),
-                     "r"(G5_TMEM_COLS)
+                     "r"(TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
@@ -150,8 +166,8 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_d = tmem_base_smem;
-    const uint32_t idesc = umma_idesc_f16(G5_BM, G5_BN);
-    const size_t xt_piece = (size_t)a.TT * a.KC * (G5_TILE_BYTES / 2);  // elements per split piece
+    const uint32_t idesc = umma_idesc_f16(G5_BM, BN);
+    const size_t xt_piece = (size_t)a.TT * a.KC * (XTILE / 2);  // elements per split piece
     const int kc_begin = blockIdx.z * a.KCs, kc_end = min(a.KC, kc_begin + a.KCs);
     unsigned char *xs_base = smem + (size_t)G5_STAGES * G5_WSTAGE_BYTES;
 
@@ -159,39 +175,47 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
         // =========== control warp: X tiles by TMA one k-step ahead, MMA issue as soon as W and X are in ===========
         if (lane == 0) {
             auto fetch_x = [&](int kc_f) {  // the three split pieces of X for k-step kc_f
-                const int xs = (kc_f - kc_begin) % G5_XSTAGES;
-                mbar_expect_tx(&full_bar[xs], G5_XPIECES * G5_TILE_BYTES);
+                const int xs = (kc_f - kc_begin) % XSTAGES;
+                mbar_expect_tx(&full_bar[xs], G5_XPIECES * XTILE);
 #pragma unroll
                 for (int p = 0; p < G5_XPIECES; ++p) {
-                    const __half *src = a.xt + p * xt_piece + ((size_t)tt * a.KC + kc_f) * (G5_TILE_BYTES / 2);
-                    bulk_g2s(xs_base + (size_t)xs * G5_XSTAGE_BYTES + p * G5_TILE_BYTES, src, G5_TILE_BYTES, &full_bar[xs]);
+                    const __half *src = a.xt + p * xt_piece + ((size_t)tt * a.KC + kc_f) * (XTILE / 2);
+                    bulk_g2s(xs_base + (size_t)xs * XSTAGE_BYTES + p * XTILE, src, XTILE, &full_bar[xs]);
                 }
             };
             if (kc_begin < kc_end) fetch_x(kc_begin);
             for (int kc = kc_begin; kc < kc_end; ++kc) {
                 const int it = kc - kc_begin;
-                const int s = it & 1, use = it >> 1, xs = it % G5_XSTAGES;
-                if (it >= G5_STAGES) mbar_wait(&done_bar[s], (uint32_t)((use - 1) & 1));  // k-step it-2 retired: its X stage is free
-                if (kc + 1 < kc_end) fetch_x(kc + 1);
+                const int s = it & 1, use = it >> 1, xs = it % XSTAGES;
+                if (XSTAGES == 3) {
+                    if (it >= G5_STAGES) mbar_wait(&done_bar[s], (uint32_t)((use - 1) & 1));  // k-step it-2 retired: its X stage is free
+                    if (kc + 1 < kc_end) fetch_x(kc + 1);
+                }
                 mbar_wait(&wfull_bar[s], (uint32_t)(use & 1));                 // W tiles of this k-step dequantised
-                mbar_wait(&full_bar[xs], (uint32_t)((it / G5_XSTAGES) & 1));   // X tiles landed
+                mbar_wait(&full_bar[xs], (uint32_t)((it / XSTAGES) & 1));   // X tiles landed
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t base = smem_u32(smem + (size_t)s * G5_WSTAGE_BYTES);
-                const uint32_t xbase = smem_u32(xs_base + (size_t)xs * G5_XSTAGE_BYTES);
-                const uint32_t lbo = G5_BM * 16, sbo = 128;  // K-chunk stride, 8-row group stride
+                const uint32_t xbase = smem_u32(xs_base + (size_t)xs * XSTAGE_BYTES);
+                const uint32_t lbo = G5_BM * 16, xlbo = BN * 16, sbo = 128;  // K-chunk strides (W, X), 8-row group stride
 #pragma unroll
                 for (int ks = 0; ks < G5_BK / 16; ++ks) {
-                    const uint32_t koff = (uint32_t)ks * 2u * lbo;
+                    const uint32_t koff = (uint32_t)ks * 2u * lbo, xkoff = (uint32_t)ks * 2u * xlbo;
                     const uint64_t whi = umma_desc(base + 0 * G5_TILE_BYTES + koff, lbo, sbo);
                     const uint64_t wlo = umma_desc(base + 1 * G5_TILE_BYTES + koff, lbo, sbo);
-                    const uint64_t xh = umma_desc(xbase + 0 * G5_TILE_BYTES + koff, lbo, sbo);
-                    const uint64_t xm = umma_desc(xbase + 1 * G5_TILE_BYTES + koff, lbo, sbo);
+                    const uint64_t xh = umma_desc(xbase + 0 * XTILE + xkoff, xlbo, sbo);
+                    const uint64_t xm = umma_desc(xbase + 1 * XTILE + xkoff, xlbo, sbo);
                     // smallest terms first
                     umma_f16(tmem_d, wlo, xh, idesc, (it | ks) != 0);
                     umma_f16(tmem_d, whi, xm, idesc, 1);
                     umma_f16(tmem_d, whi, xh, idesc, 1);
                 }
                 umma_commit(&done_bar[s]);
+                if (XSTAGES == 2 && kc + 1 < kc_end) {
+                    // two X stages: step it+1 reuses the stage of step it-1 -- fetch it once that step has retired, AFTER
+                    // this step's MMAs are queued (the tensor pipe stays busy while the copy is in flight)
+                    if (it >= 1) mbar_wait(&done_bar[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
+                    fetch_x(kc + 1);
+                }
             }
         }
     } else {
@@ -206,37 +230,44 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
             q_cur = __ldg(a.qs + blk);
             d_cur = __ldg(a.ds + blk);
         }
-        const __half2 c1032 = __half2half2(__ushort_as_half((unsigned short)0x6408));  // 1032 = 1024 + 8
-        const __half2 wsc = __float2half2_rn(G5_WSCALE);
         for (int kc = kc_begin; kc < kc_end; ++kc) {
             const int it = kc - kc_begin;
             const int s = it & 1, use = it >> 1;
             unsigned char *stage = smem + (size_t)s * G5_WSTAGE_BYTES;
             const uint4 q = q_cur;
-            const __half2 d2 = __hmul2(__half2half2(d_cur), wsc);  // d * 2^8, exact
+            // d * 2^8 (the weights' MMA scale) * 2^-112 (f16 <- f32 exponent re-bias, see g5_pack_f16x2): exact power-of-two
+            // scalings of the f16 block scale (one conversion per block; f32 denormals are NOT flushed in this file)
+            const float dd = __half2float(d_cur) * G5_WSCALE * 1.92592994438723585305597794258492732e-34f;  // 2^-112
             if (gn < a.N && kc + 1 < kc_end) {  // next k-step's block: its L2 latency hides behind this step
                 const size_t blk = (size_t)gn * bpr + (size_t)(kc + 1) * 2 + dblk;
                 q_cur = __ldg(a.qs + blk);
                 d_cur = __ldg(a.ds + blk);
             }
-            // 16 weights of the block: low nibbles (elements 0..15, dhalf = 0) or high nibbles (16..31).  All in half2 on the
-            // FMA pipe: nibble n -> half(1024 + n) by OR-ing 0x6400 (ulp = 1 there) -> n - 8 = h - 1032 (exact) ->
-            // hi = RN(n8 * d') (HMUL2), lo = n8 * d' - hi (HFMA2; the residual of an f16 product is representable)
+            // 16 weights of the block: low nibbles (elements 0..15, dhalf = 0) or high nibbles (16..31), as f16 hi + lo.
+            // Half2 arithmetic and float<->half conversions execute on the quarter-rate XU pipe on this part (ncu: the
+            // round-2a HMUL2/HFMA2 version kept XU at 103 % and the tensor pipe at 48 %), so everything stays on the FMA and
+            // ALU pipes: nibble -> float by OR-ing 0x4B000000 (2^23 + n), w' = (n - 8) * d'' in f32, Veltkamp split
+            // hi' = RN_11bit(w') (c = w' * 8193; hi' = c - (c - w')), lo' = w' - hi' (exact), and the f16 bit patterns of
+            // hi' * 2^112, lo' * 2^112 by shifts and masks (both are exactly representable: no rounding to do).
             const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
             uint32_t ph[8], pl[8];
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
-                const uint32_t nib = (dhalf ? (w4[wi] >> 4) : w4[wi]) & 0x0F0F0F0Fu;   // bytes = elements 4wi .. 4wi+3
+                const uint32_t nib = dhalf ? (w4[wi] >> 4) : w4[wi];
+                float hi[4], lo[4];
 #pragma unroll
-                for (int pr = 0; pr < 2; ++pr) {
-                    uint32_t hb;   // {0x6400 | n_(2pr), 0x6400 | n_(2pr+1)}
-                    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(hb) : "r"(nib), "r"(0x64646464u), "r"(pr ? 0x4342u : 0x4140u));
-                    const __half2 n8 = __hsub2(*reinterpret_cast<const __half2 *>(&hb), c1032);
-                    const __half2 hi = __hmul2(n8, d2);
-                    const __half2 lo = __hfma2(n8, d2, __hneg2(hi));
-                    ph[wi * 2 + pr] = *reinterpret_cast<const uint32_t *>(&hi);
-                    pl[wi * 2 + pr] = *reinterpret_cast<const uint32_t *>(&lo);
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t n = (nib >> (8 * t)) & 0xFu;
+                    // _rn intrinsics: the splitting must not be contracted into FMAs
+                    const float w = __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | n), 8388616.0f), dd);
+                    const float c = __fmul_rn(w, 8193.0f);
+                    hi[t] = __fsub_rn(c, __fsub_rn(c, w));
+                    lo[t] = __fsub_rn(w, hi[t]);
                 }
+                ph[wi * 2 + 0] = g5_pack_f16x2(hi[0], hi[1]);
+                ph[wi * 2 + 1] = g5_pack_f16x2(hi[2], hi[3]);
+                pl[wi * 2 + 0] = g5_pack_f16x2(lo[0], lo[1]);
+                pl[wi * 2 + 1] = g5_pack_f16x2(lo[2], lo[3]);
             }
             if (it >= G5_STAGES) {
                 mbar_wait(&done_bar[s], (uint32_t)((use - 1) & 1));  // MMAs that read this W stage have retired
@@ -264,16 +295,17 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
         }
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     }
-    // ---- epilogue: dequant warp w reads TMEM lanes 32*(w%4).. (features), columns 32*(w/4).. (tokens)
+    // ---- epilogue: dequant warp w reads TMEM lanes 32*(w%4).. (features), columns 32*(w/4) + 128*h .. (tokens)
     {
         __shared__ int is_last;
+        constexpr int NH = BN / 128;
         const bool ew = warp < G5_DQ_WARPS;  // the control warp only joins the barriers
-        const int q4 = warp & 3, col0 = (warp >> 2) * 32;
+        const int q4 = warp & 3;
         const int feat = f0 + q4 * 32 + lane;
         const int tile_id = blockIdx.y * gridDim.x + blockIdx.x, n_tile = gridDim.x * gridDim.y;
-        float *ptile = a.SK > 1 ? a.partial + ((size_t)blockIdx.z * n_tile + tile_id) * (G5_BM * G5_BN) : nullptr;
+        float *ptile = a.SK > 1 ? a.partial + ((size_t)blockIdx.z * n_tile + tile_id) * (G5_BM * BN) : nullptr;
         uint32_t r[32];
-        if (ew) {
+        auto load_tmem = [&](int col0) {
             const uint32_t taddr = tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -284,38 +316,8 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
                   "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        }
-        bool run_epilogue = true;
-        if (a.SK > 1) {
-            // publish this slice's tile, take a ticket; the last arriver sums the slices in order
-            if (ew) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) __stcg(ptile + (size_t)(col0 + j) * G5_BM + q4 * 32 + lane, __uint_as_float(r[j]));
-            }
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                const int old = atomicAdd(&a.counters[tile_id], 1);
-                const int last = (old == a.SK - 1);
-                if (last) {
-                    a.counters[tile_id] = 0;
-                    __threadfence();
-                }
-                is_last = last;
-            }
-            __syncthreads();
-            run_epilogue = is_last != 0;
-            if (run_epilogue && ew) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float v = 0.0f;
-                    for (int z = 0; z < a.SK; ++z)
-                        v += __ldcg(a.partial + ((size_t)z * n_tile + tile_id) * (G5_BM * G5_BN) + (size_t)(col0 + j) * G5_BM + q4 * 32 + lane);
-                    r[j] = __float_as_uint(v);
-                }
-            }
-        }
-        if (run_epilogue && ew) {
+        };
+        auto emit = [&](int col0) {   // bias / residual / activation of the 32 token columns in r
             const float bsv = (a.bias && feat < a.N) ? a.bias[feat] : 0.0f;
             const float my_sc = a.oscale[tok0 + col0 + lane];   // token column col0 + lane; broadcast per column below
 #pragma unroll
@@ -334,12 +336,53 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
                     a.y[(size_t)tok * a.ldy + feat] = v;
                 }
             }
+        };
+        if (a.SK <= 1) {
+            if (ew)
+                for (int h = 0; h < NH; ++h) {
+                    const int col0 = (warp >> 2) * 32 + h * 128;
+                    load_tmem(col0);
+                    emit(col0);
+                }
+        } else {
+            // publish this slice's tile, take a ticket; the last arriver sums the slices in order
+            if (ew)
+                for (int h = 0; h < NH; ++h) {
+                    const int col0 = (warp >> 2) * 32 + h * 128;
+                    load_tmem(col0);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) __stcg(ptile + (size_t)(col0 + j) * G5_BM + q4 * 32 + lane, __uint_as_float(r[j]));
+                }
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                const int old = atomicAdd(&a.counters[tile_id], 1);
+                const int last = (old == a.SK - 1);
+                if (last) {
+                    a.counters[tile_id] = 0;
+                    __threadfence();
+                }
+                is_last = last;
+            }
+            __syncthreads();
+            if (is_last != 0 && ew)
+                for (int h = 0; h < NH; ++h) {
+                    const int col0 = (warp >> 2) * 32 + h * 128;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float v = 0.0f;
+                        for (int z = 0; z < a.SK; ++z)
+                            v += __ldcg(a.partial + ((size_t)z * n_tile + tile_id) * (G5_BM * BN) + (size_t)(col0 + j) * G5_BM + q4 * 32 + lane);
+                        r[j] = __float_as_uint(v);
+                    }
+                    emit(col0);
+                }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(G5_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -349,7 +392,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
 // written as zeros.
 __global__ void __launch_bounds__(256) split_tiles_kernel(const float *__restrict__ x, int M, int K, const float *__restrict__ gamma,
                                                           const float *__restrict__ ada, float eps, __half *__restrict__ xt,
-                                                          float *__restrict__ oscale, int TT, int KC) {
+                                                          float *__restrict__ oscale, int TT, int KC, int BN) {
     __shared__ float ssq_part[32][8], max_part[32][8];
     __shared__ float rms_s[8], sc_s[8];
     const int r8 = threadIdx.x & 7, cth = threadIdx.x >> 3;  // cth: 0..31 strides over the 16-byte chunks
@@ -397,8 +440,9 @@ __global__ void __launch_bounds__(256) split_tiles_kernel(const float *__restric
         __syncthreads();
     }
     const float rms = rms_s[r8], sc = sc_s[r8];
-    const int tt = row / G5_BN, rin = row % G5_BN;
-    const size_t piece = (size_t)TT * KC * (G5_TILE_BYTES / 2);
+    const int tt = row / BN, rin = row % BN;
+    const size_t tile_el = (size_t)BN * G5_BK;   // f16 elements of one (token tile, k-step) tile
+    const size_t piece = (size_t)TT * KC * tile_el;
     for (int c = cth; c < nchunk; c += 32) {
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (valid) {
@@ -423,8 +467,8 @@ __global__ void __launch_bounds__(256) split_tiles_kernel(const float *__restric
             p[0][e] = *reinterpret_cast<const uint32_t *>(&h);
             p[1][e] = *reinterpret_cast<const uint32_t *>(&m);
         }
-        // tile (tt, kc = c/8), chunk-in-tile c%8, row rin: [8][128][16 B]
-        const size_t off = ((size_t)tt * KC + (c >> 3)) * (G5_TILE_BYTES / 2) + (size_t)((c & 7) * G5_BN + rin) * 8;
+        // tile (tt, kc = c/8), chunk-in-tile c%8, row rin: [8][BN][16 B]
+        const size_t off = ((size_t)tt * KC + (c >> 3)) * tile_el + (size_t)((c & 7) * BN + rin) * 8;
 #pragma unroll
         for (int s = 0; s < G5_XPIECES; ++s)
             *reinterpret_cast<uint4 *>(xt + s * piece + off) = make_uint4(p[s][0], p[s][1], p[s][2], p[s][3]);
@@ -437,12 +481,18 @@ bool gemm_tc5_supported(const Q4Weight &w, int M) { return w.N % G5_BM == 0 && w
 
 // f16 elements of the split buffer: two pieces of tiles + the per-token output scales (floats) behind them
 static size_t g5_tiles_elems(int M, int K) {
-    const size_t TT = (size_t)(M + G5_BN - 1) / G5_BN;
-    return G5_XPIECES * TT * (size_t)(K / G5_BK) * (G5_TILE_BYTES / 2);
+    const int BN = g5_bn(M);
+    const size_t TT = (size_t)(M + BN - 1) / BN;
+    return G5_XPIECES * TT * (size_t)(K / G5_BK) * ((size_t)BN * G5_BK);
 }
 size_t gemm_tc5_split_elems(int M, int K) {
-    const size_t TT = (size_t)(M + G5_BN - 1) / G5_BN;
-    return g5_tiles_elems(M, K) + 2 * TT * G5_BN + 8;
+    // callers size one buffer for the largest (M, K) they use: take the worse of the two tile widths
+    size_t worst = 0;
+    for (int BN : {128, 256}) {
+        const size_t TT = (size_t)(M + BN - 1) / BN;
+        worst = std::max(worst, G5_XPIECES * TT * (size_t)(K / G5_BK) * ((size_t)BN * G5_BK) + 2 * TT * BN + 16);
+    }
+    return worst;
 }
 static float *g5_oscale_ptr(void *xt, int M, int K) {
     size_t off = g5_tiles_elems(M, K) * 2;          // bytes
@@ -454,8 +504,9 @@ static float *g5_oscale_ptr(void *xt, int M, int K) {
 void launch_split_tiles(const float *x, int M, int K, const float *gamma, const float *ada, float eps, void *xt,
                         cudaStream_t st) {
     VOX_CHECK(K % G5_BK == 0, VOX_EINVAL, "split_tiles: K=%d not a multiple of 64", K);
-    const int TT = (M + G5_BN - 1) / G5_BN, KC = K / G5_BK;
-    split_tiles_kernel<<<TT * (G5_BN / 8), 256, 0, st>>>(x, M, K, gamma, ada, eps, (__half *)xt, g5_oscale_ptr(xt, M, K), TT, KC);
+    const int BN = g5_bn(M);
+    const int TT = (M + BN - 1) / BN, KC = K / G5_BK;
+    split_tiles_kernel<<<TT * (BN / 8), 256, 0, st>>>(x, M, K, gamma, ada, eps, (__half *)xt, g5_oscale_ptr(xt, M, K), TT, KC, BN);
     tc_count_launch("split_tiles");
 }
 
@@ -470,13 +521,14 @@ void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int 
     a.M = M;
     a.xt = (const __half *)xt;
     a.oscale = g5_oscale_ptr(const_cast<void *>(xt), M, w.K);
-    a.TT = (M + G5_BN - 1) / G5_BN;
+    const int BN = g5_bn(M);
+    a.TT = (M + BN - 1) / BN;
     a.KC = w.K / G5_BK;
     a.y = y;
     a.ldy = ldy;
     a.bias = bias;
     a.res = res;
-    const size_t smem = (size_t)G5_SMEM_BYTES + 1024;
+    const size_t smem = (size_t)g5_smem_bytes(BN) + 1024;
     // split K when the output tiles alone cannot fill the GPU (single-stream encode: N = 1280 -> 50 tiles;
     // prefill: 38 tokens -> one token tile)
     const int tiles = (w.N / G5_BM) * a.TT;
@@ -485,7 +537,7 @@ void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int 
         SK = 148 / tiles;
         SK = SK > 8 ? 8 : SK;
         while (SK > 1 && a.KC / SK < 4) --SK;
-        while (SK > 1 && ((size_t)SK * tiles * G5_BM * G5_BN > gw->partial_floats || tiles > gw->n_counters)) --SK;
+        while (SK > 1 && ((size_t)SK * tiles * G5_BM * BN > gw->partial_floats || tiles > gw->n_counters)) --SK;
     }
     a.KCs = (a.KC + SK - 1) / SK;
     SK = (a.KC + a.KCs - 1) / a.KCs;
@@ -495,9 +547,15 @@ void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int 
     dim3 grid(w.N / G5_BM, a.TT, SK);
 #define G5_CASE(E)                                                                                              \
     case E: {                                                                                                   \
-        static SmemAttr attr;                                                                                   \
-        smem_attr_check(ensure_dyn_smem(gemm_tc5_kernel<E>, smem, attr), "gemm_tc5");                           \
-        gemm_tc5_kernel<E><<<grid, G5_THREADS, smem, st>>>(a);                                                  \
+        if (BN == 256) {                                                                                        \
+            static SmemAttr attr;                                                                               \
+            smem_attr_check(ensure_dyn_smem(gemm_tc5_kernel<E, 256>, smem, attr), "gemm_tc5");                  \
+            gemm_tc5_kernel<E, 256><<<grid, G5_THREADS, smem, st>>>(a);                                         \
+        } else {                                                                                                \
+            static SmemAttr attr;                                                                               \
+            smem_attr_check(ensure_dyn_smem(gemm_tc5_kernel<E, 128>, smem, attr), "gemm_tc5");                  \
+            gemm_tc5_kernel<E, 128><<<grid, G5_THREADS, smem, st>>>(a);                                         \
+        }                                                                                                       \
         break;                                                                                                  \
     }
     switch (epi) {

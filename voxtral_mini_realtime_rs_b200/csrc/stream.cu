@@ -431,6 +431,46 @@ void StreamPool::tick(vox_stream_stats *st_out) {
     if (st_out) *st_out = stats;
 }
 
+// Q4VoxtralModel::encode_audio_with_cache (model.rs:790-799) = Q4AudioEncoder::forward_with_cache (437-452: conv stem on
+// the chunk alone, layers extend the caches) + reshape_encoder_output + adapter.
+int StreamPool::encode_chunk(int id, const float *mel, int T, float *out, size_t cap) {
+    const vox_model_info &c = m->info;
+    Slot &sl = slot(id);
+    VOX_CHECK(sl.n_samples == pad_left(pad) && sl.n_audio == 0, VOX_EINVAL, "stream session %d is fed by push(): do not mix with encode_chunk", id);
+    VOX_CHECK(T >= 1 && T <= s->max_mel_frames, VOX_EINVAL, "mel chunk of %d frames exceeds the pool's capacity %d", T, s->max_mel_frames);
+    CUDA_OK(cudaSetDevice(m->device));
+    const int d = c.enc_dim, D = c.dec_dim, rf = c.reshape_factor;
+    const int T1 = conv_out(T), S = conv_out(T1), S4 = S / rf;
+    VOX_CHECK(sl.n_enc + S <= m->enc_rope_len, VOX_ECAPACITY, "encoder positions %d exceed the RoPE table (%d)", sl.n_enc + S, m->enc_rope_len);
+    VOX_CHECK(cap >= (size_t)S4 * D, VOX_ECAPACITY, "audio_embeds capacity %zu < %zu", cap, (size_t)S4 * D);
+    CUDA_OK(cudaMemcpyAsync(s->mel, mel, sizeof(float) * (size_t)c.n_mels * T, cudaMemcpyHostToDevice, s->st));
+    launch_transpose_mel(s->mel, s->mel_tm, 1, c.n_mels, T, s->st);
+    launch_conv2_gemm(s->mel_tm, m->conv1_w, m->conv1_b, s->h1, 1, T, T1, c.n_mels, d, s->st);
+    // rows beyond the ring slack go through the layers in several passes; the conv output of the whole chunk waits in
+    // the session's (otherwise unused in chunk mode) encoder-output region
+    float *conv = enc_out + (size_t)id * s->S_max * d;
+    launch_conv2_gemm(s->h1, m->conv2_w, m->conv2_b, conv, 1, T1, S, d, d, s->st);
+    for (int r0 = 0; r0 < S; r0 += max_new) {
+        const int R = std::min(max_new, S - r0);
+        std::vector<int> rs(R, id), rp(R);
+        for (int i = 0; i < R; ++i) rp[i] = sl.n_enc + r0 + i;
+        CUDA_OK(cudaMemcpyAsync(s->x_enc, conv + (size_t)r0 * d, sizeof(float) * (size_t)R * d, cudaMemcpyDeviceToDevice, s->st));
+        CUDA_OK(cudaMemcpyAsync(d_row_slot, rs.data(), sizeof(int) * R, cudaMemcpyHostToDevice, s->st));
+        CUDA_OK(cudaMemcpyAsync(d_row_pos, rp.data(), sizeof(int) * R, cudaMemcpyHostToDevice, s->st));
+        CUDA_OK(cudaStreamSynchronize(s->st));
+        encoder_rows(R);
+        CUDA_OK(cudaMemcpyAsync(s->packed + (size_t)r0 * d, s->h_enc, sizeof(float) * (size_t)R * d, cudaMemcpyDeviceToDevice, s->st));
+    }
+    sl.n_enc += S;
+    if (S4 > 0) {
+        s->linear(m->adapter0, s->packed, S4, s->adapter_h, D, nullptr, nullptr, EPI_GELU);
+        s->linear(m->adapter2, s->adapter_h, S4, s->audio, D, nullptr, nullptr, EPI_NONE);
+        CUDA_OK(cudaMemcpyAsync(out, s->audio, sizeof(float) * (size_t)S4 * D, cudaMemcpyDeviceToHost, s->st));
+    }
+    CUDA_OK(cudaStreamSynchronize(s->st));
+    return S4;
+}
+
 int StreamPool::final_enc(const Slot &sl) const {
     int64_t tg[5];
     stream_progress(sl.n_samples, true, m->info.reshape_factor, m->info.prefix_len, tg);

@@ -40,6 +40,10 @@ struct StreamPool {
     void tick(vox_stream_stats *stats);
     size_t poll(int id, int32_t *ids, size_t cap, bool *done);
     const float *audio_embeds(int id, int *n);   // device pointer [n][dec_dim]
+    // encode_audio_with_cache (model.rs:790-799): one mel chunk [128][T] (host) through the conv stem ON ITS OWN (zero
+    // padding at the chunk edges, as upstream) and the encoder layers over the session's K/V rings; returns the
+    // chunk's S/4 audio embeddings (host, [n][dec_dim]).  For sessions driven chunk-wise instead of push()/tick().
+    int encode_chunk(int id, const float *mel, int T, float *out, size_t cap_floats);
 
   private:
     Slot &slot(int id);
