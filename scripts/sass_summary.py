@@ -56,8 +56,19 @@ def main():
     print(f"# {os.path.relpath(LIB, ROOT)}: {len(counts)} kernels, architectures {sorted(set(arch))}")
     print(f"# columns: instructions, registers, then counts of {' '.join(KEYS)} (zeros omitted)")
     for k, c in counts.items():
-        name = re.sub(r"\(.*", "", dm.get(k, k)).replace("vox::(anonymous namespace)::", "").replace("vox::", "")
+        name = dm.get(k, k).replace("vox::(anonymous namespace)::", "").replace("(anonymous namespace)::", "").replace("vox::", "")
         name = re.sub(r"^void ", "", name)
+        # strip the parameter list (the last top-level parenthesis group), keep template arguments
+        depth, cut = 0, len(name)
+        for i in range(len(name) - 1, -1, -1):
+            if name[i] == ")":
+                depth += 1
+            elif name[i] == "(":
+                depth -= 1
+                if depth == 0:
+                    cut = i
+                    break
+        name = name[:cut]
         hits = " ".join(f"{key}={c[key]}" for key in KEYS if c[key])
         print(f"{name:70s} instr={c['_total']:6d} regs={regs.get(k, 0):3d}  {hits}")
 

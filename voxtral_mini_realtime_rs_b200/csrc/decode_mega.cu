@@ -69,8 +69,6 @@ __host__ __device__ constexpr int mg_misc_bytes(int MT) {
     return ((432 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT + 4 * mg_vals(MT)) + 127) & ~127;
 }
 __host__ __device__ constexpr int mg_pair_bytes(int MT) { return 272 * MT; }  // fragments + offsets of one block pair
-// keys staged per bulk-copy batch in the attention phase (K and V: 2 * KB * hd floats of the scratch region)
-__host__ __device__ constexpr int mg_attn_kb(int MT) { return MT >= 4 ? 64 : 16; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -745,10 +743,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             float *red_m = kvs + 2 * HD;                           // [MG_CWARPS][G]
             float *red_l = red_m + MG_CWARPS * G;                  // [MG_CWARPS][G]
             float *red_acc = red_l + MG_CWARPS * G;                // [MG_CWARPS][G][HD]
-            // the unit's cached keys / values, bulk-copied page run by page run: [KB][HD] each.  Aliases red_acc (the
-            // warps' partial states are written only after the last batch has been consumed)
-            constexpr int KB = mg_attn_kb(MT);
-            float *Ks = red_acc, *Vs = red_acc + KB * HD;
             const int H = p.H, Hkv = p.Hkv, max_seq = p.max_seq, NC = p.attn_chunks;
             KvView kvw;
             kvw.k = op.kc;
@@ -765,22 +759,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 const int j0 = j_lo + ch * per, j1 = min(pos + 1, j0 + per);  // keys [j0, j1)
                 const bool has_new = j0 <= pos && pos < j1;                    // this chunk holds the new row
                 const float *row = p.qkv + (size_t)b * p.ld_qkv;
-                const int jc1 = min(j1, pos);   // cached keys [j0, jc1); the new row `pos` (has_new) is consumed from kvs
-                auto issue_kv = [&](const int jb0) {   // bulk copies of up to KB cached keys / values into Ks / Vs
-                    const int nkb = min(KB, jc1 - jb0);
-                    if (nkb <= 0) return;
-                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic accesses of the region precede
-                    mbar_expect_tx(stg, (uint32_t)nkb * HD * 8u);
-                    for (int a = jb0; a < jb0 + nkb;) {   // runs inside one page are contiguous
-                        const int pg = a / KV_PAGE, e = min(jb0 + nkb, (pg + 1) * KV_PAGE);
-                        const size_t off = (((size_t)p.page_table[(size_t)b * p.max_pages + pg] * Hkv + kvh) * KV_PAGE + (a - pg * KV_PAGE)) * HD;
-                        bulk_g2s(Ks + (size_t)(a - jb0) * HD, kvw.k + off, (uint32_t)(e - a) * HD * 4u, stg);
-                        bulk_g2s(Vs + (size_t)(a - jb0) * HD, kvw.v + off, (uint32_t)(e - a) * HD * 4u, stg);
-                        a = e;
-                    }
-                };
                 cbar();  // scratch free (previous unit / previous op)
-                if (tid == 0) issue_kv(j0);  // in flight while q, k, v are fetched and rotated
                 // q (G heads) and k through RoPE on the way in (rope.rs:103-141: interleaved pairs), v as is
                 constexpr int half = HD / 2;
                 for (int i = tid; i < (G + 1) * half; i += MG_CTHREADS) {
@@ -816,28 +795,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
 #pragma unroll
                     for (int i = 0; i < DPL; ++i) acc[h][i] = 0.0f;
                 }
-                constexpr int KU = 4;  // keys per warp per softmax rescale
-                // cached keys are staged in shared memory KB at a time by bulk copies (one latency per batch instead of one per
-                // warp round)
-                for (int jb0 = j0; jb0 < jc1 || (has_new && jb0 == j0 && jc1 <= j0); jb0 += KB) {
-                    const int nkb = max(0, min(KB, jc1 - jb0));
-                    if (jb0 > j0) {
-                        cbar();  // every warp is done with the previous batch
-                        if (tid == 0) issue_kv(jb0);
-                    }
-                    if (nkb > 0) {
-                        mbar_wait(stg, stg_phase, wd_flag, 0x700u + (unsigned)oi);
-                        stg_phase ^= 1u;
-                    }
-                    const bool last_batch = jb0 + KB >= jc1;
-                    const int nk = nkb + ((has_new && last_batch) ? 1 : 0);   // the new row rides with the last batch
-                    for (int i0 = warp; i0 < nk; i0 += KU * MG_CWARPS) {
-                        float kk[KU][DPL], vv[KU][DPL];
+                constexpr int KU = 4;  // keys in flight per warp; one softmax rescale per KU keys
+                for (int jb = j0 + warp; jb < j1; jb += KU * MG_CWARPS) {
+                    float kk[KU][DPL], vv[KU][DPL];
 #pragma unroll
-                        for (int u = 0; u < KU; ++u) {
-                            const int i = i0 + u * MG_CWARPS;
-                            const float *kr = (i < nkb) ? Ks + (size_t)i * HD + lane * DPL : kvs + lane * DPL;
-                            const float *vr = (i < nkb) ? Vs + (size_t)i * HD + lane * DPL : kvs + HD + lane * DPL;
+                    for (int u = 0; u < KU; ++u) {
+                        const int j = jb + u * MG_CWARPS;
+                        if (j < j1 && j != pos) {
+                            const size_t at = kv_index(kvw, b, Hkv, kvh, j, HD) + lane * DPL;
+                            const float *kr = kvw.k + at;
+                            const float *vr = kvw.v + at;
                             if constexpr (DPL == 4) {
                                 const float4 k4 = *reinterpret_cast<const float4 *>(kr);
                                 const float4 v4 = *reinterpret_cast<const float4 *>(vr);
@@ -845,57 +812,61 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                                 vv[u][0] = v4.x; vv[u][1] = v4.y; vv[u][2] = v4.z; vv[u][3] = v4.w;
                             } else {
 #pragma unroll
-                                for (int q2 = 0; q2 < DPL; ++q2) {
-                                    kk[u][q2] = kr[q2];
-                                    vv[u][q2] = vr[q2];
+                                for (int i = 0; i < DPL; ++i) {
+                                    kk[u][i] = kr[i];
+                                    vv[u][i] = vr[i];
                                 }
                             }
-                        }
-                        float sc[KU][G];
+                        } else {  // j == pos: the row appended above, still in shared memory (j >= j1: unused)
 #pragma unroll
-                        for (int u = 0; u < KU; ++u)
-#pragma unroll
-                            for (int h = 0; h < G; ++h) {
-                                float d = 0.0f;
-#pragma unroll
-                                for (int q2 = 0; q2 < DPL; ++q2) d = fmaf(q[h][q2], kk[u][q2], d);
-                                sc[u][h] = d;
-                            }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                            for (int u = 0; u < KU; ++u)
-#pragma unroll
-                                for (int h = 0; h < G; ++h) sc[u][h] += __shfl_xor_sync(0xffffffffu, sc[u][h], o);
-#pragma unroll
-                        for (int h = 0; h < G; ++h) {
-                            float m_new = m_run[h];
-#pragma unroll
-                            for (int u = 0; u < KU; ++u) {
-                                sc[u][h] = (i0 + u * MG_CWARPS < nk) ? sc[u][h] * p.scale : -INFINITY;
-                                m_new = fmaxf(m_new, sc[u][h]);
-                            }
-                            const float alpha = fast_exp(m_run[h] - m_new);  // exp(-inf) = 0 on the first batch
-                            float pe[KU], ps = 0.0f;
-#pragma unroll
-                            for (int u = 0; u < KU; ++u) {
-                                pe[u] = fast_exp(sc[u][h] - m_new);  // masked keys: exp(-inf) = 0
-                                ps += pe[u];
-                            }
-                            l_run[h] = l_run[h] * alpha + ps;
-                            m_run[h] = m_new;
-#pragma unroll
-                            for (int q2 = 0; q2 < DPL; ++q2) {
-                                float a2 = acc[h][q2] * alpha;
-#pragma unroll
-                                for (int u = 0; u < KU; ++u) a2 = fmaf(pe[u], vv[u][q2], a2);
-                                acc[h][q2] = a2;
+                            for (int i = 0; i < DPL; ++i) {
+                                kk[u][i] = kvs[lane * DPL + i];
+                                vv[u][i] = kvs[HD + lane * DPL + i];
                             }
                         }
                     }
-                    if (last_batch) break;
+                    float sc[KU][G];
+#pragma unroll
+                    for (int u = 0; u < KU; ++u)
+#pragma unroll
+                        for (int h = 0; h < G; ++h) {
+                            float d = 0.0f;
+#pragma unroll
+                            for (int i = 0; i < DPL; ++i) d = fmaf(q[h][i], kk[u][i], d);
+                            sc[u][h] = d;
+                        }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int u = 0; u < KU; ++u)
+#pragma unroll
+                            for (int h = 0; h < G; ++h) sc[u][h] += __shfl_xor_sync(0xffffffffu, sc[u][h], o);
+#pragma unroll
+                    for (int h = 0; h < G; ++h) {
+                        float m_new = m_run[h];
+#pragma unroll
+                        for (int u = 0; u < KU; ++u) {
+                            sc[u][h] = (jb + u * MG_CWARPS < j1) ? sc[u][h] * p.scale : -INFINITY;
+                            m_new = fmaxf(m_new, sc[u][h]);
+                        }
+                        const float alpha = fast_exp(m_run[h] - m_new);  // exp(-inf) = 0 on the first batch
+                        float pe[KU], ps = 0.0f;
+#pragma unroll
+                        for (int u = 0; u < KU; ++u) {
+                            pe[u] = fast_exp(sc[u][h] - m_new);  // masked keys: exp(-inf) = 0
+                            ps += pe[u];
+                        }
+                        l_run[h] = l_run[h] * alpha + ps;
+                        m_run[h] = m_new;
+#pragma unroll
+                        for (int i = 0; i < DPL; ++i) {
+                            float a = acc[h][i] * alpha;
+#pragma unroll
+                            for (int u = 0; u < KU; ++u) a = fmaf(pe[u], vv[u][i], a);
+                            acc[h][i] = a;
+                        }
+                    }
                 }
-                cbar();  // K/V staging is dead: its space becomes the warps' partial states
                 if (tracing) p.trace[oi * 6 + 4] = (unsigned long long)clock64();
 #pragma unroll
                 for (int h = 0; h < G; ++h) {
@@ -1158,8 +1129,7 @@ MegaPlan decode_mega_plan(int B, int max_pairs, int H, int Hkv, int hd) {
     MegaPlan pl;
     pl.MT = B <= 1 ? 1 : (B <= 2 ? 2 : (B <= 4 ? 4 : 8));
     const int G = H / Hkv;
-    const int kv_stage = 2 * mg_attn_kb(pl.MT) * hd, red = MG_CWARPS * G * hd;   // aliased: the larger one
-    const int attn_bytes = ((G + 2) * hd + 2 * MG_CWARPS * G + (kv_stage > red ? kv_stage : red)) * (int)sizeof(float);
+    const int attn_bytes = ((G + 2) * hd + 2 * MG_CWARPS * G + MG_CWARPS * G * hd) * (int)sizeof(float);
     const int per_pair = mg_pair_bytes(pl.MT);
     int cap_pairs = MG_SCRATCH_CAP / per_pair;
     if (cap_pairs >= MG_CHUNK) cap_pairs = cap_pairs / MG_CHUNK * MG_CHUNK;

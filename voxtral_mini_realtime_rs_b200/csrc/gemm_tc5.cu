@@ -24,6 +24,7 @@
 //   * epilogue: tcgen05.ld 32 lanes x 32 columns per warp; lane = feature, so every column is a
 //     coalesced 128-byte store of Y[token][f0+32q .. +31]; bias / residual / GELU / SiLU*up fused.
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -136,6 +137,7 @@ struct G5Args {
     int SK, KCs;
     float *partial;
     int *counters;
+    int debug;   // VOX_G5_DEBUG experiments (garbage results): 1 = X tiles fetched for the first k-steps only, 2 = no dequant arithmetic
 };
 
 template <int EPI, int BN>
@@ -176,6 +178,10 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
         if (lane == 0) {
             auto fetch_x = [&](int kc_f) {  // the three split pieces of X for k-step kc_f
                 const int xs = (kc_f - kc_begin) % XSTAGES;
+                if ((a.debug & 1) && kc_f - kc_begin >= XSTAGES) {   // experiment: no further X traffic
+                    mbar_arrive(&full_bar[xs]);
+                    return;
+                }
                 mbar_expect_tx(&full_bar[xs], G5_XPIECES * XTILE);
 #pragma unroll
                 for (int p = 0; p < G5_XPIECES; ++p) {
@@ -251,6 +257,10 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gemm_tc5_kernel(const G5Args a)
             // hi' * 2^112, lo' * 2^112 by shifts and masks (both are exactly representable: no rounding to do).
             const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
             uint32_t ph[8], pl[8];
+            if (a.debug & 2) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) ph[e] = pl[e] = w4[e & 3];
+            } else
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
                 const uint32_t nib = dhalf ? (w4[wi] >> 4) : w4[wi];
@@ -542,6 +552,10 @@ void launch_q4_gemm_tc5(const Q4Weight &w, const void *xt, int M, float *y, int 
     a.KCs = (a.KC + SK - 1) / SK;
     SK = (a.KC + a.KCs - 1) / a.KCs;
     a.SK = SK;
+    {
+        static const int dbg = getenv("VOX_G5_DEBUG") ? atoi(getenv("VOX_G5_DEBUG")) : 0;
+        a.debug = dbg;
+    }
     a.partial = SK > 1 ? gw->partial : nullptr;
     a.counters = SK > 1 ? gw->counters : nullptr;
     dim3 grid(w.N / G5_BM, a.TT, SK);
