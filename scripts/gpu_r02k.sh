@@ -1,0 +1,8 @@
+#!/bin/bash
+# block-scale conversion on the ALU pipes: phase trace + parity
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 300 python scripts/mega_trace.py --streams 8 > gpurun_out/mega_trace_r02k_b8.txt 2>&1; tail -12 gpurun_out/mega_trace_r02k_b8.txt
+timeout 300 python scripts/mega_trace.py --streams 1 > gpurun_out/mega_trace_r02k_b1.txt 2>&1; tail -12 gpurun_out/mega_trace_r02k_b1.txt
+timeout 300 python scripts/mega_trace.py --streams 4 > gpurun_out/mega_trace_r02k_b4.txt 2>&1; tail -12 gpurun_out/mega_trace_r02k_b4.txt
+timeout 900 python -m pytest tests/test_model_gpu.py tests/test_golden_gpu.py tests/test_kernels_gpu.py -m gpu -x -q -s 2>&1 | grep -E "\[ids\]|passed|failed|Error|error|assert" | tail -20

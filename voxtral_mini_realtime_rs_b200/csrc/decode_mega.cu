@@ -145,6 +145,42 @@ __device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gm
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
         : "memory");
 }
+// ---- 2-CTA cluster helpers (fragment multicast): remote mbarrier arrive, cluster-scope wait, multicast bulk copy
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t peer_rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(smem_u32(bar)), "r"(peer_rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity, unsigned *flag, unsigned code) {
+    if (mbar_try_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    unsigned n = 0;
+    while (!mbar_try_cluster(bar, parity)) {
+        if ((++n & 0x3FFFu) == 0 && clock64() - t0 > MG_SPIN_CYCLES) mg_die(flag, code);
+    }
+}
+// one L2 read, delivered to the same shared-memory offset of every CTA in `mask`; each destination's mbarrier (same offset)
+// receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_mc(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
 // barrier among the first NW warps (the epilogue warps of a matvec phase)
 template <int NW>
 __device__ __forceinline__ void rbar() {
@@ -255,7 +291,7 @@ __device__ __forceinline__ void frag_build(const float4 l, const float4 h, const
 template <int MT, int NT, int NTV>
 __device__ __forceinline__ void mg_pair(const unsigned char *__restrict__ sb, const uint32_t slot_q, const uint32_t slot_d,
                                         const uint2 *__restrict__ bfp, const float2 *__restrict__ ofp, const int g, const int t,
-                                        const int lane, float (&acc)[NT][2 * ((MT + 3) / 4)]) {
+                                        const int lane, float (&acc)[NT][2 * ((MT + 3) / 4)], uint64_t *release) {
     constexpr int CG = (MT + 3) / 4;
     uint4 wq[NTV];
     uint2 wd[NTV];
@@ -264,27 +300,47 @@ __device__ __forceinline__ void mg_pair(const unsigned char *__restrict__ sb, co
         wq[u] = *reinterpret_cast<const uint4 *>(sb + (size_t)u * MG_SLOT_BYTES + slot_q);
         wd[u] = *reinterpret_cast<const uint2 *>(sb + (size_t)u * MG_SLOT_BYTES + slot_d);
     }
+    // the warp's share of the stage is in registers: hand the stage back to the producer BEFORE the arithmetic (the ring
+    // is only a few stages deep at 8 tokens -- the refill latency, not the MMAs, then sets the pace)
+    if (release != nullptr) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(release);
+    }
 #pragma unroll
     for (int bb = 0; bb < 2; ++bb) {
         if constexpr (MT == 8) {
             const uint4 *bq = reinterpret_cast<const uint4 *>(bfp + (size_t)bb * (16 * MT));
             const uint4 fh = bq[lane], fm = bq[32 + lane];  // {b0,b1} of the low-nibble half, {b0,b1} of the high-nibble half
             const float4 o = *reinterpret_cast<const float4 *>(ofp + bb * MT + 2 * t);  // {off, inv} of tokens 2t, 2t+1
+            // the tiles' accumulation chains are interleaved MMA by MMA: a chained m16n8k16 waits ~33 cycles for its
+            // predecessor, the asm statements keep their source order, and one chain after the other left the warp idle
+            // for most of that latency
+            uint32_t al[NTV][4], ah[NTV][4];
+            float cc[NTV][4];
 #pragma unroll
             for (int u = 0; u < NTV; ++u) {
                 const uint32_t wg = bb ? wq[u].z : wq[u].x, wg8 = bb ? wq[u].w : wq[u].y;
+                const uint32_t sg = wg >> 8, sg8 = wg8 >> 8;
+                al[u][0] = wg & 0x000F000Fu; al[u][1] = wg8 & 0x000F000Fu; al[u][2] = sg & 0x000F000Fu; al[u][3] = sg8 & 0x000F000Fu;
+                ah[u][0] = wg & 0x00F000F0u; ah[u][1] = wg8 & 0x00F000F0u; ah[u][2] = sg & 0x00F000F0u; ah[u][3] = sg8 & 0x00F000F0u;
+                cc[u][0] = cc[u][1] = cc[u][2] = cc[u][3] = 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < NTV; ++u) mma16816(cc[u], al[u][0], al[u][1], al[u][2], al[u][3], fh.x, fh.y);
+#pragma unroll
+            for (int u = 0; u < NTV; ++u) mma16816(cc[u], ah[u][0], ah[u][1], ah[u][2], ah[u][3], fh.z, fh.w);
+#pragma unroll
+            for (int u = 0; u < NTV; ++u) mma16816(cc[u], al[u][0], al[u][1], al[u][2], al[u][3], fm.x, fm.y);
+#pragma unroll
+            for (int u = 0; u < NTV; ++u) mma16816(cc[u], ah[u][0], ah[u][1], ah[u][2], ah[u][3], fm.z, fm.w);
+#pragma unroll
+            for (int u = 0; u < NTV; ++u) {
                 const uint32_t dw = bb ? wd[u].y : wd[u].x;
                 const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&dw));
-                const uint32_t sg = wg >> 8, sg8 = wg8 >> 8;
-                float cc[4] = {0.f, 0.f, 0.f, 0.f};
-                mma16816(cc, wg & 0x000F000Fu, wg8 & 0x000F000Fu, sg & 0x000F000Fu, sg8 & 0x000F000Fu, fh.x, fh.y);
-                mma16816(cc, wg & 0x00F000F0u, wg8 & 0x00F000F0u, sg & 0x00F000F0u, sg8 & 0x00F000F0u, fh.z, fh.w);
-                mma16816(cc, wg & 0x000F000Fu, wg8 & 0x000F000Fu, sg & 0x000F000Fu, sg8 & 0x000F000Fu, fm.x, fm.y);
-                mma16816(cc, wg & 0x00F000F0u, wg8 & 0x00F000F0u, sg & 0x00F000F0u, sg8 & 0x00F000F0u, fm.z, fm.w);
-                acc[u][0] = fmaf(d.x, fmaf(cc[0], o.y, o.x), acc[u][0]);
-                acc[u][1] = fmaf(d.x, fmaf(cc[1], o.w, o.z), acc[u][1]);
-                acc[u][2] = fmaf(d.y, fmaf(cc[2], o.y, o.x), acc[u][2]);
-                acc[u][3] = fmaf(d.y, fmaf(cc[3], o.w, o.z), acc[u][3]);
+                acc[u][0] = fmaf(d.x, fmaf(cc[u][0], o.y, o.x), acc[u][0]);
+                acc[u][1] = fmaf(d.x, fmaf(cc[u][1], o.w, o.z), acc[u][1]);
+                acc[u][2] = fmaf(d.y, fmaf(cc[u][2], o.y, o.x), acc[u][2]);
+                acc[u][3] = fmaf(d.y, fmaf(cc[u][3], o.w, o.z), acc[u][3]);
             }
         } else {
             const uint2 *bfb = bfp + (size_t)(bb * 2) * (2 * MT) * 4;
@@ -336,6 +392,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     float *acc_tile = red + 2 * MG_CWARPS * NT * 16 * MT;             // [MG_ACC_TILES][16*MT]
     float *vals = acc_tile + MG_ACC_TILES * 16 * MT;                  // [1 or 2 blocks][32][MT]
     uint64_t *stg = empty + MG_MAX_STAGES;                            // activation fragments landed in scratch
+    uint64_t *pfree = stg + 1;                                        // cluster peer's scratch is free (2-CTA multicast)
     unsigned char *scratch = smem + mg_misc_bytes(MT);
     unsigned char *ring = scratch + p.scratch_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -350,6 +407,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             mbar_init(&empty[i], MG_CWARPS);
         }
         mbar_init(stg, 1);
+        mbar_init(pfree, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -414,7 +472,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     // =========================== consumers ===========================
     const int epoch = *p.d_epoch;  // decode steps run by this session so far (attention chunk flags)
     int stage = 0;
-    uint32_t phase = 0, stg_phase = 0;
+    uint32_t phase = 0, stg_phase = 0, pf_phase = 0;
+    const bool early_release = !(p.flags & 32);  // flag 32: experiment -- release a stage after the arithmetic
+    const bool clus = p.cluster2 != 0;          // launched as 2-CTA clusters: (cta, cta ^ 1) share every fragment copy
     int par = 0;
     unsigned bar_target = 0;
     float best_v = -INFINITY;
@@ -465,40 +525,59 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             const int n_tiles = op.n_tiles, n_pairs = op.n_pairs, S = op.S, Ps = op.Ps, N = op.N, K = op.K;
             const int epi = op.epi, ldy = op.ldy, track = op.track_argmax, UT = op.unit_tiles;
             const bool has_norm = op.gamma != nullptr;
-            float *const yout = op.y;
+            float *const yout = (op.track_argmax && p.logits_out) ? p.logits_out : op.y;
             const float *const bias = op.bias, *const resid = op.res;
             float *const ssq_out = op.ssq_out;
             uint2 *const fout_bf = op.fout_bf;
             float2 *const fout_off = op.fout_off;
             const float *const fout_gamma = op.fout_gamma;
             const int ntl = mg_tile_count(n_tiles, UT, cta, nctas);
+            // in a 2-CTA cluster both CTAs stage (and receive) the fragments if either has tiles in this phase
+            const bool stage_any = ntl > 0 || (clus && mg_tile_count(n_tiles, UT, cta ^ 1, nctas) > 0);
             float2 *off2 = reinterpret_cast<float2 *>(scratch);             // [2*Ps][MT]
             uint2 *bf = reinterpret_cast<uint2 *>(off2 + (size_t)Ps * 2 * MT);  // [2*Ps][2][2*MT][4]
-            if (ntl > 0) {
+            if (stage_any) {
                 for (int s = 0; s < S; ++s) {
                     const int pb = s * Ps;
                     const int np = min(Ps, n_pairs - pb);
                     cbar();  // every warp is done with the previous contents of scratch
                     if (tid == 0) {
+                        if (clus) {   // the peer's scratch must be free as well: its half of the copy lands in mine and vice versa
+                            mbar_arrive_remote(pfree, (uint32_t)((cta & 1) ^ 1));
+                            mbar_wait_cluster(pfree, pf_phase, wd_flag, 0x800u + (unsigned)oi);
+                        }
                         // the input's fragments were written (generic proxy, other SMs) before the grid barrier
                         asm volatile("fence.proxy.async;\n" ::: "memory");
                         const uint32_t ob = (uint32_t)(2 * np * MT) * 8u, bb = (uint32_t)(2 * np * MT) * 128u;
                         mbar_expect_tx(stg, ob + bb);
-                        bulk_g2s(off2, op.fin_off + (size_t)(2 * pb) * MT, ob, stg);
-                        // every CTA copies the same fragments: start each CTA at a different eighth so that the 148
-                        // copies do not sweep the same L2 slices in lock step
                         const unsigned char *src = reinterpret_cast<const unsigned char *>(op.fin_bf + (size_t)(2 * pb) * (16 * MT));
                         unsigned char *dstb = reinterpret_cast<unsigned char *>(bf);
-                        if ((p.flags & 8) || bb < 8u * 1024u) {
-                            bulk_g2s(dstb, src, bb, stg);
-                        } else {
+                        if (clus) {
+                            // every fragment byte is read from L2 ONCE per CTA pair: rank r copies the eighths q with
+                            // q % 2 == r (rank 0 also the offsets) and multicasts them to both CTAs
+                            const int rank = cta & 1;
+                            if (rank == 0) bulk_g2s_mc(off2, op.fin_off + (size_t)(2 * pb) * MT, ob, stg, (uint16_t)3);
                             const uint32_t chunk = ((bb / 8u) + 15u) & ~15u;
-                            for (int q = 0; q < 8; ++q) {
-                                const uint32_t o = (uint32_t)((q + cta) & 7) * chunk;
-                                if (o < bb) bulk_g2s(dstb + o, src + o, min(chunk, bb - o), stg);
+                            for (int q = rank; q < 8; q += 2) {
+                                const uint32_t o = (uint32_t)q * chunk;
+                                if (o < bb) bulk_g2s_mc(dstb + o, src + o, min(chunk, bb - o), stg, (uint16_t)3);
+                            }
+                        } else {
+                            bulk_g2s(off2, op.fin_off + (size_t)(2 * pb) * MT, ob, stg);
+                            // every CTA copies the same fragments: start each CTA at a different eighth so that the 148
+                            // copies do not sweep the same L2 slices in lock step
+                            if ((p.flags & 8) || bb < 8u * 1024u) {
+                                bulk_g2s(dstb, src, bb, stg);
+                            } else {
+                                const uint32_t chunk = ((bb / 8u) + 15u) & ~15u;
+                                for (int q = 0; q < 8; ++q) {
+                                    const uint32_t o = (uint32_t)((q + cta) & 7) * chunk;
+                                    if (o < bb) bulk_g2s(dstb + o, src + o, min(chunk, bb - o), stg);
+                                }
                             }
                         }
                     }
+                    if (clus) pf_phase ^= 1u;
                     // row statistics of the fused RMSNorm (first used by the epilogue)
                     if (s == 0 && has_norm && warp < B) {
                         float ss = 0.0f;
@@ -577,13 +656,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                                     const unsigned char *sb = ring + (size_t)stage * (NT * MG_SLOT_BYTES);
                                     const uint2 *bfp = bf + (size_t)pp * (2 * 16 * MT);
                                     const float2 *ofp = off2 + (size_t)pp * (2 * MT);
-                                    if (nt == NT) mg_pair<MT, NT, NT>(sb, slot_q, slot_d, bfp, ofp, g, t, lane, acc);
-                                    else if (NT > 1 && nt == 1) mg_pair<MT, NT, 1>(sb, slot_q, slot_d, bfp, ofp, g, t, lane, acc);
-                                    else if (NT > 2 && nt == 2) mg_pair<MT, NT, 2>(sb, slot_q, slot_d, bfp, ofp, g, t, lane, acc);
-                                    else if (NT > 3 && nt == 3) mg_pair<MT, NT, 3>(sb, slot_q, slot_d, bfp, ofp, g, t, lane, acc);
+                                    uint64_t *rel = early_release ? &empty[stage] : nullptr;
+                                    if (nt == NT) mg_pair<MT, NT, NT>(sb, slot_q, slot_d, bfp, ofp, g, t, lane, acc, rel);
+                                    else if (NT > 1 && nt == 1) mg_pair<MT, NT, 1>(sb, slot_q, slot_d, bfp, ofp, g, t, lane, acc, rel);
+                                    else if (NT > 2 && nt == 2) mg_pair<MT, NT, 2>(sb, slot_q, slot_d, bfp, ofp, g, t, lane, acc, rel);
+                                    else if (NT > 3 && nt == 3) mg_pair<MT, NT, 3>(sb, slot_q, slot_d, bfp, ofp, g, t, lane, acc, rel);
+                                    if (!early_release) {
+                                        __syncwarp();
+                                        if (lane == 0) mbar_arrive(&empty[stage]);
+                                    }
+                                } else {
+                                    __syncwarp();
+                                    if (lane == 0) mbar_arrive(&empty[stage]);
                                 }
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(&empty[stage]);
                                 if (++stage == nstage) {
                                     stage = 0;
                                     phase ^= 1u;
@@ -1100,11 +1185,19 @@ void launch_t(const MegaParams &p, const MegaPlan &plan, int grid, cudaStream_t 
     cfg.blockDim = dim3(MG_THREADS);
     cfg.dynamicSmemBytes = plan.smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (p.cluster2) {
+        VOX_CHECK(grid % 2 == 0, VOX_EINVAL, "decode_mega: 2-CTA clusters need an even grid (%d)", grid);
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
     cuda_check_mg(cudaLaunchKernelEx(&cfg, decode_mega_kernel<MT, G, DPL>, p), "decode_mega launch");
     tc_count_launch("decode_mega");
 }

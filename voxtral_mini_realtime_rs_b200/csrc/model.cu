@@ -842,7 +842,38 @@ bool Session::mega_prepare(int B) {
 // 26 layers, lm_head, argmax, device-side feedback; all positions read from device counters.
 void Session::decode_step(int B, bool add_audio) {
     const vox_model_info &c = m->info;
-    if (mega_prepare(B)) {
+    // More than 8 rows: the rows are independent streams, so the step runs as consecutive launches of the persistent
+    // kernel over groups of 8 rows (each group streams the weights once: ~2.3 ms per 8 rows, against ~12 ms for one
+    // pass of the per-op tcgen05 GEMMs at 16-32 rows -- profiles/README.md).  The scratch activations are reused by the
+    // groups; the per-row state (token, positions, page table, audio row, output row, logits) is addressed from the
+    // group's first row.
+    const int rows_per_launch = B > 8 ? 8 : B;
+    if (mega_prepare(rows_per_launch)) {
+        for (int b0 = 0; b0 < B; b0 += 8) decode_step_mega(b0, std::min(8, B - b0), add_audio);
+        return;
+    }
+    launch_embed(m->tok_emb, d_tok, add_audio ? audio : nullptr, cur_S4, B, 1, d_pos, x_dec, fused_decode(B) ? ssq_x : nullptr, st,
+                 add_audio ? audio_rows_dev : nullptr);
+    const bool pending = decoder_forward(B, 1);
+    lm_head_rows(B, pending, logits);
+    launch_argmax_multi(logits, B, c.vocab, d_tok, stream_mode ? nullptr : d_out, out_ld, d_outpos, am_vals, am_idx, am_cnt, st);
+    launch_advance(d_pos, 1, d_outpos, 1, B, st);
+}
+
+// One launch of the persistent kernel for rows [b0, b0 + B) (B <= 8) of the session; mega_prepare() has built the op table.
+void Session::decode_step_mega(int b0, int B, bool add_audio) {
+    const vox_model_info &c = m->info;
+    {
+        if (B < mega_B) {
+            // a ragged last group on the 8-token instantiation: its padding tokens must read as zero fragments, not as
+            // the previous group's rows
+            CUDA_OK(cudaMemsetAsync(mega_xf_bf, 0, sizeof(uint2) * mega_xf_blocks * 16 * 8, st));
+            CUDA_OK(cudaMemsetAsync(mega_af_bf, 0, sizeof(uint2) * mega_af_blocks * 16 * 8, st));
+            CUDA_OK(cudaMemsetAsync(mega_cf_bf, 0, sizeof(uint2) * mega_cf_blocks * 16 * 8, st));
+            CUDA_OK(cudaMemsetAsync(mega_xf_off, 0, sizeof(float2) * mega_xf_blocks * 8, st));
+            CUDA_OK(cudaMemsetAsync(mega_af_off, 0, sizeof(float2) * mega_af_blocks * 8, st));
+            CUDA_OK(cudaMemsetAsync(mega_cf_off, 0, sizeof(float2) * mega_cf_blocks * 8, st));
+        }
         MegaParams p;
         p.ops = mega_ops;
         p.n_ops = mega_n_ops;
@@ -854,7 +885,7 @@ void Session::decode_step(int B, bool add_audio) {
         p.Hkv = c.dec_kv_heads;
         p.hd = c.dec_head_dim;
         p.max_seq = out_ld;
-        p.page_table = d_page_table;
+        p.page_table = d_page_table + (size_t)b0 * kv_max_pages;
         p.max_pages = kv_max_pages;
         p.window = c.dec_window;
         p.scale = powf((float)c.dec_head_dim, -0.5f);
@@ -873,8 +904,8 @@ void Session::decode_step(int B, bool add_audio) {
         p.emb_qs = m->tok_emb.qs;
         p.emb_d = m->tok_emb.d;
         p.D = c.dec_dim;
-        p.audio = add_audio ? audio : nullptr;
-        p.audio_rows = add_audio ? audio_rows_dev : nullptr;
+        p.audio = add_audio && audio ? audio + (size_t)b0 * cur_S4 * c.dec_dim : nullptr;
+        p.audio_rows = add_audio && audio_rows_dev ? audio_rows_dev + b0 : nullptr;
         p.audio_seq = cur_S4;
         p.x_dec = x_dec;
         p.ssq_x = ssq_x;
@@ -883,11 +914,12 @@ void Session::decode_step(int B, bool add_audio) {
         p.emb_gamma = m->dec[0].attn_norm;
         p.att_fbf = mega_af_bf;
         p.att_foff = mega_af_off;
-        p.d_pos = d_pos;
-        p.d_outpos = d_outpos;
-        p.d_tok = d_tok;
-        p.d_out = stream_mode ? nullptr : d_out;
+        p.d_pos = d_pos + b0;
+        p.d_outpos = d_outpos + b0;
+        p.d_tok = d_tok + b0;
+        p.d_out = stream_mode ? nullptr : d_out + (size_t)b0 * out_ld;
         p.out_ld = out_ld;
+        p.logits_out = logits + (size_t)b0 * c.vocab;
         p.am_vals = mega_am_vals;
         p.am_idx = mega_am_idx;
         p.bar = mega_bar;
@@ -899,16 +931,11 @@ void Session::decode_step(int B, bool add_audio) {
         {
             static const int env_flags = getenv("VOX_MEGA_FLAGS") ? atoi(getenv("VOX_MEGA_FLAGS")) : 0;
             p.flags = env_flags;
+            static const int env_cluster = getenv("VOX_MEGA_CLUSTER") ? atoi(getenv("VOX_MEGA_CLUSTER")) : 0;
+            p.cluster2 = env_cluster && (mega_grid % 2 == 0);
         }
         launch_decode_mega(p, mega_plan, mega_grid, st);
-        return;
     }
-    launch_embed(m->tok_emb, d_tok, add_audio ? audio : nullptr, cur_S4, B, 1, d_pos, x_dec, fused_decode(B) ? ssq_x : nullptr, st,
-                 add_audio ? audio_rows_dev : nullptr);
-    const bool pending = decoder_forward(B, 1);
-    lm_head_rows(B, pending, logits);
-    launch_argmax_multi(logits, B, c.vocab, d_tok, stream_mode ? nullptr : d_out, out_ld, d_outpos, am_vals, am_idx, am_cnt, st);
-    launch_advance(d_pos, 1, d_outpos, 1, B, st);
 }
 
 // Prefill of M positions for B streams (model.rs:894-923 with M = 38; also the incremental vox_prefill).

@@ -157,6 +157,7 @@ struct Session {
     unsigned long long *mega_trace = nullptr;  // [mega_ops_cap][6] SM-clock stamps of CTA 0 (debug "mega_trace")
     bool mega_prepare(int B);
     bool fused_decode(int rows) const;
+    void decode_step_mega(int b0, int B, bool add_audio);
     void *xt_buf = nullptr;   // bf16 split tiles feeding the tcgen05 GEMM
     size_t xt_elems = 0;
     GemmWork gemm_work;       // split-K scratch of the tcgen05 GEMM
