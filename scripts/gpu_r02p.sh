@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 300 python scripts/mega_trace.py --streams 8 > gpurun_out/mega_trace_r02p_b8.txt 2>&1; head -1 gpurun_out/mega_trace_r02p_b8.txt; grep -E "qkv|attn|wo " gpurun_out/mega_trace_r02p_b8.txt
+VOX_MEGA_FLAGS=64 timeout 300 python scripts/mega_trace.py --streams 8 > gpurun_out/mega_trace_r02p_b8_f64.txt 2>&1; head -1 gpurun_out/mega_trace_r02p_b8_f64.txt; grep -E "qkv|attn|wo " gpurun_out/mega_trace_r02p_b8_f64.txt
+timeout 300 python scripts/mega_trace.py --streams 1 > gpurun_out/mega_trace_r02p_b1.txt 2>&1; head -1 gpurun_out/mega_trace_r02p_b1.txt; grep -E "qkv|attn|wo " gpurun_out/mega_trace_r02p_b1.txt
+VOX_MEGA_FLAGS=64 timeout 300 python scripts/mega_trace.py --streams 1 > gpurun_out/mega_trace_r02p_b1_f64.txt 2>&1; head -1 gpurun_out/mega_trace_r02p_b1_f64.txt; grep -E "qkv|attn|wo " gpurun_out/mega_trace_r02p_b1_f64.txt
+timeout 900 python -m pytest tests/test_model_gpu.py tests/test_golden_gpu.py tests/test_stream_gpu.py -m gpu -x -q -s 2>&1 | grep -E "\[ids\]|passed|failed|Error|error|assert" | tail -20

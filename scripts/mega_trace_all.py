@@ -75,12 +75,12 @@ def main():
     tw = model.debug("mega_trace_w")
     if tw is not None:
         tw = tw.reshape(16, 6, 8)
-        print("warp-level trace, CTA 0, lm_head phase (SM cycles since the first stamp): per group = start, stage1, stage2, stage3 ready, "
-              "body done, group barrier passed, epilogue done")
+        print("warp-level trace, CTA 0, op " + os.environ.get("VOX_MEGA_TRACE_W_OP", "lm_head") + " (SM cycles since the first stamp): per group = start, "
+              "stage1, stage2, stage3 ready, body done, group barrier passed, epilogue done, (reducers) partials summed")
         for gidx in range(6):
             print(f" group {gidx}")
             for w in range(16):
-                print("   w%02d " % w + " ".join(f"{int(v):7d}" for v in tw[w, gidx, :7]))
+                print("   w%02d " % w + " ".join(f"{int(v):7d}" for v in tw[w, gidx, :8]))
 
 
 if __name__ == "__main__":

@@ -64,9 +64,9 @@ __host__ __device__ constexpr int mg_vals(int MT) { return (MT <= 2 ? 2 : 1) * 3
 static_assert(mg_vals(1) >= 2 * mg_nt(1) * 1 && mg_vals(2) >= 2 * mg_nt(2) * 2 && mg_vals(4) >= 2 * mg_nt(4) * 4 &&
                   mg_vals(8) >= 2 * mg_nt(8) * 8,
               "vals also holds the lm_head phase's per-slot argmax candidates");
-// barriers + rinv + red[2][16 warps][NT*16*MT] + acc_tile[MG_ACC_TILES][16*MT] + vals
+// barriers + rinv + rpart[4][8] + stgc[4] + s_pos[8] + s_pt[64] + red[2][16 warps][NT*16*MT] + acc_tile[MG_ACC_TILES][16*MT] + vals
 __host__ __device__ constexpr int mg_misc_bytes(int MT) {
-    return ((432 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT + 4 * mg_vals(MT)) + 127) & ~127;
+    return ((880 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT + 4 * mg_vals(MT)) + 127) & ~127;
 }
 __host__ __device__ constexpr int mg_pair_bytes(int MT) { return 272 * MT; }  // fragments + offsets of one block pair
 
@@ -143,42 +143,6 @@ __device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gm
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
             smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-        : "memory");
-}
-// ---- 2-CTA cluster helpers (fragment multicast): remote mbarrier arrive, cluster-scope wait, multicast bulk copy
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t peer_rank) {
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(smem_u32(bar)), "r"(peer_rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(remote) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_cluster(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity, unsigned *flag, unsigned code) {
-    if (mbar_try_cluster(bar, parity)) return;
-    const long long t0 = clock64();
-    unsigned n = 0;
-    while (!mbar_try_cluster(bar, parity)) {
-        if ((++n & 0x3FFFu) == 0 && clock64() - t0 > MG_SPIN_CYCLES) mg_die(flag, code);
-    }
-}
-// one L2 read, delivered to the same shared-memory offset of every CTA in `mask`; each destination's mbarrier (same offset)
-// receives the complete_tx
-__device__ __forceinline__ void bulk_g2s_mc(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
         : "memory");
 }
 // barrier among the first NW warps (the epilogue warps of a matvec phase)
@@ -388,11 +352,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + MG_MAX_STAGES;
     float *rinv = reinterpret_cast<float *>(empty + MG_MAX_STAGES + 2);  // [8]
-    float *red = rinv + 8;                                            // [2][MG_CWARPS][NT*16*MT]
+    float *rpart = rinv + 8;                                          // [4 warps][8 tokens] partial sums of squares
+    uint64_t *stgc = reinterpret_cast<uint64_t *>(rpart + 32);        // [4] activation fragments of K chunk c landed in scratch
+    int *s_pos = reinterpret_cast<int *>(stgc + 4);                   // [8] the rows' positions at kernel entry
+    int *s_pt = s_pos + 8;                                            // [64] page-table row of this CTA's attention unit
+    float *red = reinterpret_cast<float *>(s_pt + 64);                                          // [2][MG_CWARPS][NT*16*MT]
     float *acc_tile = red + 2 * MG_CWARPS * NT * 16 * MT;             // [MG_ACC_TILES][16*MT]
     float *vals = acc_tile + MG_ACC_TILES * 16 * MT;                  // [1 or 2 blocks][32][MT]
     uint64_t *stg = empty + MG_MAX_STAGES;                            // activation fragments landed in scratch
-    uint64_t *pfree = stg + 1;                                        // cluster peer's scratch is free (2-CTA multicast)
     unsigned char *scratch = smem + mg_misc_bytes(MT);
     unsigned char *ring = scratch + p.scratch_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -407,7 +374,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             mbar_init(&empty[i], MG_CWARPS);
         }
         mbar_init(stg, 1);
-        mbar_init(pfree, 1);
+        for (int c = 0; c < 4; ++c) mbar_init(&stgc[c], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -472,9 +439,20 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     // =========================== consumers ===========================
     const int epoch = *p.d_epoch;  // decode steps run by this session so far (attention chunk flags)
     int stage = 0;
-    uint32_t phase = 0, stg_phase = 0, pf_phase = 0;
+    uint32_t phase = 0, stg_phase = 0;
+    // The rows' positions and the page-table row of this CTA's attention unit (unit index == cta: there is never more than
+    // one unit per CTA when B * Hkv * chunks <= grid) are constant for the whole launch: read them once, so that the
+    // attention phases start their K/V loads without a chain of dependent global loads (position -> page -> key).
+    const bool pt_cached = p.max_pages <= 64 && cta < p.B * p.Hkv * p.attn_chunks;
+    {
+        if (tid < 8) s_pos[tid] = tid < p.B ? p.d_pos[tid] : 0;
+        if (pt_cached) {
+            const int b_u = (cta / p.attn_chunks) / p.Hkv;
+            for (int i = tid; i < p.max_pages; i += MG_CTHREADS) s_pt[i] = p.page_table[(size_t)b_u * p.max_pages + i];
+        }
+        cbar();
+    }
     const bool early_release = !(p.flags & 32);  // flag 32: experiment -- release a stage after the arithmetic
-    const bool clus = p.cluster2 != 0;          // launched as 2-CTA clusters: (cta, cta ^ 1) share every fragment copy
     int par = 0;
     unsigned bar_target = 0;
     float best_v = -INFINITY;
@@ -499,7 +477,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             prefetch_l1(reinterpret_cast<const unsigned char *>(&p.ops[oi + 1]) + 128);
         }
         if (kind == MG_MATVEC) {
-            if (tid == 0 && oi + 1 < p.n_ops && !(p.flags & 2)) {
+            // (issued by warp 5's first lane: thread 0 issues the fragment copies and must not wait on the page table first)
+            if (tid == 5 * 32 && oi + 1 < p.n_ops && !(p.flags & 2)) {
                 // the next phase is this layer's attention: pull this CTA's chunk of the KV cache into L2 now, so the
                 // walk does not wait on DRAM behind the weight stream
                 const MegaOp &nx = p.ops[oi + 1];
@@ -532,71 +511,57 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             float2 *const fout_off = op.fout_off;
             const float *const fout_gamma = op.fout_gamma;
             const int ntl = mg_tile_count(n_tiles, UT, cta, nctas);
-            // in a 2-CTA cluster both CTAs stage (and receive) the fragments if either has tiles in this phase
-            const bool stage_any = ntl > 0 || (clus && mg_tile_count(n_tiles, UT, cta ^ 1, nctas) > 0);
             float2 *off2 = reinterpret_cast<float2 *>(scratch);             // [2*Ps][MT]
             uint2 *bf = reinterpret_cast<uint2 *>(off2 + (size_t)Ps * 2 * MT);  // [2*Ps][2][2*MT][4]
-            if (stage_any) {
+            if (ntl > 0) {
                 for (int s = 0; s < S; ++s) {
                     const int pb = s * Ps;
                     const int np = min(Ps, n_pairs - pb);
-                    cbar();  // every warp is done with the previous contents of scratch
+                    // The fragments land in up to 4 K chunks (whole ring stages of 16 pairs), each with its own barrier: the
+                    // first tile group starts on chunk 0 while the rest of the copy is still in flight.
+                    const int CP = 16 * ((((np + 15) >> 4) + 3) >> 2);  // pairs per chunk
+                    cbar();  // every warp is done with the previous contents of scratch (and has seen all its chunks)
                     if (tid == 0) {
-                        if (clus) {   // the peer's scratch must be free as well: its half of the copy lands in mine and vice versa
-                            mbar_arrive_remote(pfree, (uint32_t)((cta & 1) ^ 1));
-                            mbar_wait_cluster(pfree, pf_phase, wd_flag, 0x800u + (unsigned)oi);
-                        }
                         // the input's fragments were written (generic proxy, other SMs) before the grid barrier
                         asm volatile("fence.proxy.async;\n" ::: "memory");
-                        const uint32_t ob = (uint32_t)(2 * np * MT) * 8u, bb = (uint32_t)(2 * np * MT) * 128u;
-                        mbar_expect_tx(stg, ob + bb);
+                        const uint32_t ob = (uint32_t)(2 * np * MT) * 8u;
                         const unsigned char *src = reinterpret_cast<const unsigned char *>(op.fin_bf + (size_t)(2 * pb) * (16 * MT));
                         unsigned char *dstb = reinterpret_cast<unsigned char *>(bf);
-                        if (clus) {
-                            // every fragment byte is read from L2 ONCE per CTA pair: rank r copies the eighths q with
-                            // q % 2 == r (rank 0 also the offsets) and multicasts them to both CTAs
-                            const int rank = cta & 1;
-                            if (rank == 0) bulk_g2s_mc(off2, op.fin_off + (size_t)(2 * pb) * MT, ob, stg, (uint16_t)3);
-                            const uint32_t chunk = ((bb / 8u) + 15u) & ~15u;
-                            for (int q = rank; q < 8; q += 2) {
-                                const uint32_t o = (uint32_t)q * chunk;
-                                if (o < bb) bulk_g2s_mc(dstb + o, src + o, min(chunk, bb - o), stg, (uint16_t)3);
-                            }
-                        } else {
-                            bulk_g2s(off2, op.fin_off + (size_t)(2 * pb) * MT, ob, stg);
-                            // every CTA copies the same fragments: start each CTA at a different eighth so that the 148
-                            // copies do not sweep the same L2 slices in lock step
-                            if ((p.flags & 8) || bb < 8u * 1024u) {
-                                bulk_g2s(dstb, src, bb, stg);
-                            } else {
-                                const uint32_t chunk = ((bb / 8u) + 15u) & ~15u;
-                                for (int q = 0; q < 8; ++q) {
-                                    const uint32_t o = (uint32_t)((q + cta) & 7) * chunk;
-                                    if (o < bb) bulk_g2s(dstb + o, src + o, min(chunk, bb - o), stg);
-                                }
-                            }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int p0 = min(np, c * CP), p1 = min(np, (c + 1) * CP);
+                            const uint32_t o = (uint32_t)p0 * (256u * MT), cb = (uint32_t)(p1 - p0) * (256u * MT);
+                            mbar_expect_tx(&stgc[c], cb + (c == 0 ? ob : 0u));   // an empty chunk completes at once
+                            if (c == 0) bulk_g2s(off2, op.fin_off + (size_t)(2 * pb) * MT, ob, &stgc[0]);
+                            if (cb) bulk_g2s(dstb + o, src + o, cb, &stgc[c]);
                         }
                     }
-                    if (clus) pf_phase ^= 1u;
-                    // row statistics of the fused RMSNorm (first used by the epilogue)
-                    if (s == 0 && has_norm && warp < B) {
-                        float ss = 0.0f;
-                        float pr[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const int i = lane + 32 * q;
-                            pr[q] = i < op.ssq_in_parts ? __ldcg(op.ssq_in + (size_t)i * B + warp) : 0.0f;
-                        }
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) ss += pr[q];
-                        for (int i = lane + 256; i < op.ssq_in_parts; i += 32) ss += __ldcg(op.ssq_in + (size_t)i * B + warp);
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                        if (lane == 0) rinv[warp] = 1.0f / sqrtf(ss / (float)K + p.eps);
-                    }
-                    mbar_wait(stg, stg_phase, wd_flag, 0x500u + (unsigned)oi);
+                    const uint32_t stg_par = stg_phase;
                     stg_phase ^= 1u;
-                    cbar();  // rinv visible to the epilogue threads
+                    // row statistics of the fused RMSNorm (first used by the epilogue)
+                    // The partial sums live as [part][8 tokens]: warps 1..4 read them with coalesced loads (lane % 8 = token).
+                    // (One warp per token reading its column cost 2048 sector requests per CTA for the same 6 KB -- an L2
+                    // hot spot that made the normed phases' staging 1-2.5 us longer than the others'.)
+                    if (s == 0 && has_norm && warp >= 1 && warp <= 4) {
+                        const int total = op.ssq_in_parts * 8;
+                        float pr[12];
+#pragma unroll
+                        for (int q = 0; q < 12; ++q) {
+                            const int f = (warp - 1) * 32 + lane + 128 * q;
+                            pr[q] = f < total ? __ldcg(op.ssq_in + f) : 0.0f;
+                        }
+                        float ss = 0.0f;
+#pragma unroll
+                        for (int q = 0; q < 12; ++q) ss += pr[q];
+                        for (int f = (warp - 1) * 32 + lane + 128 * 12; f < total; f += 128) ss += __ldcg(op.ssq_in + f);
+                        ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+                        ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+                        if (lane < 8) rpart[(warp - 1) * 8 + lane] = ss;
+                    }
+                    cbar();  // the warps' partial sums are visible
+                    // 1/rms per token: first read by the epilogue, i.e. behind the first tile group's CTA barrier
+                    if (s == 0 && has_norm && tid < B)
+                        rinv[tid] = 1.0f / sqrtf((((rpart[tid] + rpart[8 + tid]) + (rpart[16 + tid] + rpart[24 + tid]))) / (float)K + p.eps);
                     if (tracing && s == 0) p.trace[oi * 6 + 1] = (unsigned long long)clock64();
                     // the CTA's tiles NT at a time: every warp carries NT independent accumulation chains that
                     // share one read of the activation fragments
@@ -605,7 +570,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
 #ifdef VOX_MEGA_WARP_TRACE
                         // warp-level trace of the lm_head phase's first groups (CTA 0; debug "mega_trace_w")
                         unsigned long long *tw = nullptr;
-                        if (p.trace_w != nullptr && cta == 0 && lane == 0 && oi == p.n_ops - 2 && s == 0 && it / NT < 6)
+                        if (p.trace_w != nullptr && cta == 0 && lane == 0 && oi == (p.trace_w_op >= 0 ? p.trace_w_op : p.n_ops - 2) && s == 0 && it / NT < 6)
                             tw = p.trace_w + ((size_t)warp * 6 + it / NT) * 8;
                         if (tw) tw[0] = (unsigned long long)clock64();
 #else
@@ -647,6 +612,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                             const uint32_t slot_q = (uint32_t)warp * 512u + (uint32_t)lane * 16u;
                             const uint32_t slot_d = (uint32_t)MG_SLOT_Q + (uint32_t)warp * 64u + (uint32_t)g * 8u;
                             for (int c0 = 0; c0 < np; c0 += MG_CHUNK) {
+                                // first pass over this K slice: the fragments of this chunk must have landed
+                                if (it == 0 && c0 % CP == 0) mbar_wait(&stgc[c0 / CP], stg_par, wd_flag, 0x500u + (unsigned)oi);
                                 mbar_wait(&full[stage], phase, wd_flag, 0x200u + (unsigned)oi);
                                 if (tracing && s == 0 && it == 0 && c0 == 0) p.trace[oi * 6 + 4] = (unsigned long long)clock64();
                                 if (tr_all && s == 0 && it == 0 && c0 == 0) ta[3] = (unsigned long long)clock64();
@@ -714,6 +681,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
 #pragma unroll
                                     for (int w = 0; w < MG_CWARPS; w += 2 * st) pw[w] += pw[w + st];
                                 v = pw[0];
+                                if (tw) tw[7] = (unsigned long long)clock64();
                                 if (S > 1) {
                                     float *at = acc_tile + (size_t)(it + r_slot) * 16 * MT + (rt % (16 * MT));
                                     if (s > 0) v += *at;
@@ -746,7 +714,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                                         sq += __shfl_xor_sync(0xffffffffu, sq, 4);
                                         sq += __shfl_xor_sync(0xffffffffu, sq, 2);
                                         sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                                        if (live && r_r == 0) ssq_out[(size_t)r_tile * B + r_tok] = sq;
+                                        if (live && r_r == 0) ssq_out[(size_t)r_tile * 8 + r_tok] = sq;
                                     }
                                 }
                                 if (fout_bf) {
@@ -837,13 +805,51 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             for (int unit = cta; unit < B * Hkv * NC; unit += nctas) {
                 const int ch = unit % NC, bk = unit / NC;
                 const int b = bk / Hkv, kvh = bk - b * Hkv;
-                const int pos = p.d_pos[b];              // per row: sessions of different ages share the step
+                const int pos = s_pos[b];                // per row: sessions of different ages share the step
                 if (pos >= max_seq) continue;
                 const int j_lo = pos - p.window > 0 ? pos - p.window : 0;
                 const int per = (pos - j_lo + NC) / NC;  // ceil((pos - j_lo + 1) / NC) keys per chunk
                 const int j0 = j_lo + ch * per, j1 = min(pos + 1, j0 + per);  // keys [j0, j1)
                 const bool has_new = j0 <= pos && pos < j1;                    // this chunk holds the new row
                 const float *row = p.qkv + (size_t)b * p.ld_qkv;
+                const bool pt_s = pt_cached && unit == cta;  // the unit's page-table row is in shared memory
+                auto kv_at = [&](const int j) -> size_t {
+                    const int phys = pt_s ? s_pt[j / KV_PAGE] : kvw.page_table[(size_t)b * kvw.max_pages + (j / KV_PAGE)];
+                    return (((size_t)phys * Hkv + kvh) * KV_PAGE + (j % KV_PAGE)) * HD;
+                };
+                constexpr int KU = 4;  // keys in flight per warp; one softmax rescale per KU keys
+                float kk[KU][DPL], vv[KU][DPL];
+                // keys jb + u * 16 (u < KU) of the cache -> registers; the row being appended (j == pos) is patched in from
+                // shared memory by the caller
+                auto load_keys = [&](const int jb) {
+#pragma unroll
+                    for (int u = 0; u < KU; ++u) {
+                        const int j = jb + u * MG_CWARPS;
+                        if (j < j1 && j != pos) {
+                            const size_t at = kv_at(j) + lane * DPL;
+                            const float *kr = kvw.k + at;
+                            const float *vr = kvw.v + at;
+                            if constexpr (DPL == 4) {
+                                const float4 k4 = *reinterpret_cast<const float4 *>(kr);
+                                const float4 v4 = *reinterpret_cast<const float4 *>(vr);
+                                kk[u][0] = k4.x; kk[u][1] = k4.y; kk[u][2] = k4.z; kk[u][3] = k4.w;
+                                vv[u][0] = v4.x; vv[u][1] = v4.y; vv[u][2] = v4.z; vv[u][3] = v4.w;
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < DPL; ++i) {
+                                    kk[u][i] = kr[i];
+                                    vv[u][i] = vr[i];
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < DPL; ++i) kk[u][i] = vv[u][i] = 0.0f;
+                        }
+                    }
+                };
+                // the first batch of keys is requested BEFORE q, k, v of the new row are staged: the two round trips overlap
+                const bool kv_early = !(p.flags & 64);   // flag 64: experiment -- request them after the staging instead
+                if (kv_early && j0 + warp < j1) load_keys(j0 + warp);
                 cbar();  // scratch free (previous unit / previous op)
                 // q (G heads) and k through RoPE on the way in (rope.rs:103-141: interleaved pairs), v as is
                 constexpr int half = HD / 2;
@@ -861,7 +867,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 if (tracing) p.trace[oi * 6 + 1] = (unsigned long long)clock64();
                 if (tr_all) ta[3] = (unsigned long long)clock64();
                 if (has_new) {
-                    const size_t at = kv_index(kvw, b, Hkv, kvh, pos, HD);
+                    const size_t at = kv_at(pos);
                     for (int i = tid; i < HD; i += MG_CTHREADS) {
                         kvw.k[at + i] = kvs[i];
                         kvw.v[at + i] = kvs[HD + i];
@@ -880,29 +886,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
 #pragma unroll
                     for (int i = 0; i < DPL; ++i) acc[h][i] = 0.0f;
                 }
-                constexpr int KU = 4;  // keys in flight per warp; one softmax rescale per KU keys
                 for (int jb = j0 + warp; jb < j1; jb += KU * MG_CWARPS) {
-                    float kk[KU][DPL], vv[KU][DPL];
+                    if (!kv_early || jb != j0 + warp) load_keys(jb);
 #pragma unroll
                     for (int u = 0; u < KU; ++u) {
-                        const int j = jb + u * MG_CWARPS;
-                        if (j < j1 && j != pos) {
-                            const size_t at = kv_index(kvw, b, Hkv, kvh, j, HD) + lane * DPL;
-                            const float *kr = kvw.k + at;
-                            const float *vr = kvw.v + at;
-                            if constexpr (DPL == 4) {
-                                const float4 k4 = *reinterpret_cast<const float4 *>(kr);
-                                const float4 v4 = *reinterpret_cast<const float4 *>(vr);
-                                kk[u][0] = k4.x; kk[u][1] = k4.y; kk[u][2] = k4.z; kk[u][3] = k4.w;
-                                vv[u][0] = v4.x; vv[u][1] = v4.y; vv[u][2] = v4.z; vv[u][3] = v4.w;
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < DPL; ++i) {
-                                    kk[u][i] = kr[i];
-                                    vv[u][i] = vr[i];
-                                }
-                            }
-                        } else {  // j == pos: the row appended above, still in shared memory (j >= j1: unused)
+                        if (jb + u * MG_CWARPS == pos) {  // the row appended above, still in shared memory
 #pragma unroll
                             for (int i = 0; i < DPL; ++i) {
                                 kk[u][i] = kvs[lane * DPL + i];
@@ -1091,8 +1079,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         sh += __shfl_xor_sync(0xffffffffu, sh, o);
                     }
                     if (act && j == 0) {
-                        p.ssq_x[(size_t)(2 * blk) * B + b] = sl;
-                        p.ssq_x[(size_t)(2 * blk + 1) * B + b] = sh;
+                        p.ssq_x[(size_t)(2 * blk) * 8 + b] = sl;
+                        p.ssq_x[(size_t)(2 * blk + 1) * 8 + b] = sh;
                     }
                 }
                 cbar();
@@ -1185,19 +1173,11 @@ void launch_t(const MegaParams &p, const MegaPlan &plan, int grid, cudaStream_t 
     cfg.blockDim = dim3(MG_THREADS);
     cfg.dynamicSmemBytes = plan.smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (p.cluster2) {
-        VOX_CHECK(grid % 2 == 0, VOX_EINVAL, "decode_mega: 2-CTA clusters need an even grid (%d)", grid);
-        attr[1].id = cudaLaunchAttributeClusterDimension;
-        attr[1].val.clusterDim.x = 2;
-        attr[1].val.clusterDim.y = 1;
-        attr[1].val.clusterDim.z = 1;
-        cfg.numAttrs = 2;
-    }
     cuda_check_mg(cudaLaunchKernelEx(&cfg, decode_mega_kernel<MT, G, DPL>, p), "decode_mega launch");
     tc_count_launch("decode_mega");
 }

@@ -95,14 +95,13 @@ struct MegaParams {
     unsigned long long *trace_all = nullptr;
     // optional warp-level trace of CTA 0's first 6 tile groups of the lm_head phase: [16 warps][6 groups][8 stamps]
     unsigned long long *trace_w = nullptr;
+    int trace_w_op = -1;   // op index the warp trace records (-1: the lm_head phase)
     // experiment switches (VOX_MEGA_FLAGS): 1 no evict-first hint, 2 no KV-cache L2 prefetch, 4 no norm-weight prefetch,
     // 8 fragments copied in one piece (no per-CTA rotation), 16 weight loop without the arithmetic (garbage results:
     // measures the memory pipeline alone), 32 ring stages released after the arithmetic (instead of right after the
-    // warp's loads of the stage)
+    // warp's loads of the stage), 64 attention K/V loads issued after (not before) the staging of q, k, v
     int flags = 0;
     float *logits_out = nullptr;  // != nullptr: where the lm_head op writes its rows (row groups of a larger batch)
-    // launched as 2-CTA clusters: the activation fragments are read from L2 once per CTA pair and multicast to both
-    int cluster2 = 0;
 };
 
 struct MegaPlan {

@@ -929,10 +929,12 @@ void Session::decode_step_mega(int b0, int B, bool add_audio) {
         p.trace_all = mega_trace_all;
         p.trace_w = mega_trace_w;
         {
+            static const int env_two = getenv("VOX_MEGA_TRACE_W_OP") ? atoi(getenv("VOX_MEGA_TRACE_W_OP")) : -1;
+            p.trace_w_op = env_two;
+        }
+        {
             static const int env_flags = getenv("VOX_MEGA_FLAGS") ? atoi(getenv("VOX_MEGA_FLAGS")) : 0;
             p.flags = env_flags;
-            static const int env_cluster = getenv("VOX_MEGA_CLUSTER") ? atoi(getenv("VOX_MEGA_CLUSTER")) : 0;
-            p.cluster2 = env_cluster && (mega_grid % 2 == 0);
         }
         launch_decode_mega(p, mega_plan, mega_grid, st);
     }
