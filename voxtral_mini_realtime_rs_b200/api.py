@@ -24,7 +24,8 @@ class VoxtralError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, _LIB_NAME)
+    # VOX_LIB_PATH: load another build of the same library (A/B runs of two kernel versions on one GPU box)
+    return os.environ.get("VOX_LIB_PATH") or os.path.join(_HERE, _LIB_NAME)
 
 
 _lib = None

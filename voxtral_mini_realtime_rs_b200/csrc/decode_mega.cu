@@ -47,7 +47,12 @@ inline void cuda_check_mg(cudaError_t e, const char *what) {
 
 constexpr int MG_CWARPS = 16;                    // consumer warps
 constexpr int MG_CTHREADS = MG_CWARPS * 32;
-constexpr int MG_THREADS = MG_CTHREADS + 32;     // + the producer warp
+// + the producer's warpgroup: warp 16 is the producer, warps 17-19 exist only so that the warpgroup can hand most of its
+// registers to the consumers (setmaxnreg works on whole warpgroups of 4 warps).  The register file is allocated in units of
+// 4 warps anyway: 17 warps cost as many registers as 20.
+constexpr int MG_THREADS = MG_CTHREADS + 128;
+constexpr int MG_REGS_CONSUMER = 112;            // 16 x 32 x (112 - 96) = 8192 registers moved ...
+constexpr int MG_REGS_PRODUCER = 32;             // ... from the producer's warpgroup: 4 x 32 x (96 - 32) = 8192
 constexpr int MG_CHUNK = 16;                     // block pairs per ring stage (one per consumer warp)
 constexpr int MG_SLOT_Q = MG_CHUNK * 512;        // nibble bytes of one tile's part of a stage; its scales follow
 constexpr int MG_SLOT_BYTES = MG_CHUNK * 576;    // a stage holds NT such slots (NT tiles advance together)
@@ -64,9 +69,9 @@ __host__ __device__ constexpr int mg_vals(int MT) { return (MT <= 2 ? 2 : 1) * 3
 static_assert(mg_vals(1) >= 2 * mg_nt(1) * 1 && mg_vals(2) >= 2 * mg_nt(2) * 2 && mg_vals(4) >= 2 * mg_nt(4) * 4 &&
                   mg_vals(8) >= 2 * mg_nt(8) * 8,
               "vals also holds the lm_head phase's per-slot argmax candidates");
-// barriers + rinv + rpart[4][8] + stgc[4] + s_pos[8] + s_pt[64] + red[2][16 warps][NT*16*MT] + acc_tile[MG_ACC_TILES][16*MT] + vals
+// barriers + rinv + red[2][16 warps][NT*16*MT] + acc_tile[MG_ACC_TILES][16*MT] + vals
 __host__ __device__ constexpr int mg_misc_bytes(int MT) {
-    return ((880 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT + 4 * mg_vals(MT)) + 127) & ~127;
+    return ((432 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT + 4 * mg_vals(MT)) + 127) & ~127;
 }
 __host__ __device__ constexpr int mg_pair_bytes(int MT) { return 272 * MT; }  // fragments + offsets of one block pair
 
@@ -348,15 +353,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     static_assert(G * HD <= MG_CTHREADS, "one attention output per consumer thread");
     constexpr int NT = mg_nt(MT);
     constexpr int RW = (NT * 16 * MT + 31) / 32;  // warps that add the per-warp partial sums and run the epilogue
+    constexpr int NSETS = MG_CWARPS / RW;         // reducer sets (the role rotates from group to group)
+    static_assert(MG_CWARPS % RW == 0 && 2 * NSETS * NT * MT <= mg_vals(MT), "reducer sets tile the consumer warps; vals holds their argmax candidates");
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + MG_MAX_STAGES;
     float *rinv = reinterpret_cast<float *>(empty + MG_MAX_STAGES + 2);  // [8]
-    float *rpart = rinv + 8;                                          // [4 warps][8 tokens] partial sums of squares
-    uint64_t *stgc = reinterpret_cast<uint64_t *>(rpart + 32);        // [4] activation fragments of K chunk c landed in scratch
-    int *s_pos = reinterpret_cast<int *>(stgc + 4);                   // [8] the rows' positions at kernel entry
-    int *s_pt = s_pos + 8;                                            // [64] page-table row of this CTA's attention unit
-    float *red = reinterpret_cast<float *>(s_pt + 64);                                          // [2][MG_CWARPS][NT*16*MT]
+    float *red = rinv + 8;                                            // [2][MG_CWARPS][NT*16*MT]
     float *acc_tile = red + 2 * MG_CWARPS * NT * 16 * MT;             // [MG_ACC_TILES][16*MT]
     float *vals = acc_tile + MG_ACC_TILES * 16 * MT;                  // [1 or 2 blocks][32][MT]
     uint64_t *stg = empty + MG_MAX_STAGES;                            // activation fragments landed in scratch
@@ -374,14 +377,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             mbar_init(&empty[i], MG_CWARPS);
         }
         mbar_init(stg, 1);
-        for (int c = 0; c < 4; ++c) mbar_init(&stgc[c], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
 
+    // Register split (the launch gives every thread 96: 640 threads x 96 = 61440 of the SM's 65536).  The kernel keeps the
+    // operand fragments of the weight loop, the epilogue's prefetched operands and the op parameters live at once; at 96
+    // registers that spills, and with 227 KB of the SM's 256 KB configured as shared memory there is next to no L1 left to
+    // catch local-memory traffic: every spill reload is an L2 round trip (a build with a 256-byte frame ran the step in
+    // 3.08 ms instead of 2.27).  The producer needs few registers, the three filler warps none.
     // =========================== producer: the step's whole weight schedule ===========================
-    if (warp == MG_CWARPS) {
-        if (lane == 0) {
+    if (warp >= MG_CWARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(MG_REGS_PRODUCER));
+        if (warp == MG_CWARPS && lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             bool wrapped = false;
@@ -437,21 +445,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     }
 
     // =========================== consumers ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(MG_REGS_CONSUMER));
     const int epoch = *p.d_epoch;  // decode steps run by this session so far (attention chunk flags)
     int stage = 0;
     uint32_t phase = 0, stg_phase = 0;
-    // The rows' positions and the page-table row of this CTA's attention unit (unit index == cta: there is never more than
-    // one unit per CTA when B * Hkv * chunks <= grid) are constant for the whole launch: read them once, so that the
-    // attention phases start their K/V loads without a chain of dependent global loads (position -> page -> key).
-    const bool pt_cached = p.max_pages <= 64 && cta < p.B * p.Hkv * p.attn_chunks;
-    {
-        if (tid < 8) s_pos[tid] = tid < p.B ? p.d_pos[tid] : 0;
-        if (pt_cached) {
-            const int b_u = (cta / p.attn_chunks) / p.Hkv;
-            for (int i = tid; i < p.max_pages; i += MG_CTHREADS) s_pt[i] = p.page_table[(size_t)b_u * p.max_pages + i];
-        }
-        cbar();
-    }
+    const bool red_rotate = !(p.flags & 128);  // flag 128: experiment -- the last RW warps reduce every group (old behaviour)
+    int group_ctr = 0;
     const bool early_release = !(p.flags & 32);  // flag 32: experiment -- release a stage after the arithmetic
     int par = 0;
     unsigned bar_target = 0;
@@ -477,8 +476,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             prefetch_l1(reinterpret_cast<const unsigned char *>(&p.ops[oi + 1]) + 128);
         }
         if (kind == MG_MATVEC) {
-            // (issued by warp 5's first lane: thread 0 issues the fragment copies and must not wait on the page table first)
-            if (tid == 5 * 32 && oi + 1 < p.n_ops && !(p.flags & 2)) {
+            if (tid == 0 && oi + 1 < p.n_ops && !(p.flags & 2)) {
                 // the next phase is this layer's attention: pull this CTA's chunk of the KV cache into L2 now, so the
                 // walk does not wait on DRAM behind the weight stream
                 const MegaOp &nx = p.ops[oi + 1];
@@ -517,51 +515,46 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 for (int s = 0; s < S; ++s) {
                     const int pb = s * Ps;
                     const int np = min(Ps, n_pairs - pb);
-                    // The fragments land in up to 4 K chunks (whole ring stages of 16 pairs), each with its own barrier: the
-                    // first tile group starts on chunk 0 while the rest of the copy is still in flight.
-                    const int CP = 16 * ((((np + 15) >> 4) + 3) >> 2);  // pairs per chunk
-                    cbar();  // every warp is done with the previous contents of scratch (and has seen all its chunks)
+                    cbar();  // every warp is done with the previous contents of scratch
                     if (tid == 0) {
                         // the input's fragments were written (generic proxy, other SMs) before the grid barrier
                         asm volatile("fence.proxy.async;\n" ::: "memory");
-                        const uint32_t ob = (uint32_t)(2 * np * MT) * 8u;
+                        const uint32_t ob = (uint32_t)(2 * np * MT) * 8u, bb = (uint32_t)(2 * np * MT) * 128u;
+                        mbar_expect_tx(stg, ob + bb);
                         const unsigned char *src = reinterpret_cast<const unsigned char *>(op.fin_bf + (size_t)(2 * pb) * (16 * MT));
                         unsigned char *dstb = reinterpret_cast<unsigned char *>(bf);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int p0 = min(np, c * CP), p1 = min(np, (c + 1) * CP);
-                            const uint32_t o = (uint32_t)p0 * (256u * MT), cb = (uint32_t)(p1 - p0) * (256u * MT);
-                            mbar_expect_tx(&stgc[c], cb + (c == 0 ? ob : 0u));   // an empty chunk completes at once
-                            if (c == 0) bulk_g2s(off2, op.fin_off + (size_t)(2 * pb) * MT, ob, &stgc[0]);
-                            if (cb) bulk_g2s(dstb + o, src + o, cb, &stgc[c]);
+                        bulk_g2s(off2, op.fin_off + (size_t)(2 * pb) * MT, ob, stg);
+                        // every CTA copies the same fragments: start each CTA at a different eighth so that the 148
+                        // copies do not sweep the same L2 slices in lock step
+                        if ((p.flags & 8) || bb < 8u * 1024u) {
+                            bulk_g2s(dstb, src, bb, stg);
+                        } else {
+                            const uint32_t chunk = ((bb / 8u) + 15u) & ~15u;
+                            for (int q = 0; q < 8; ++q) {
+                                const uint32_t o = (uint32_t)((q + cta) & 7) * chunk;
+                                if (o < bb) bulk_g2s(dstb + o, src + o, min(chunk, bb - o), stg);
+                            }
                         }
                     }
-                    const uint32_t stg_par = stg_phase;
-                    stg_phase ^= 1u;
                     // row statistics of the fused RMSNorm (first used by the epilogue)
-                    // The partial sums live as [part][8 tokens]: warps 1..4 read them with coalesced loads (lane % 8 = token).
-                    // (One warp per token reading its column cost 2048 sector requests per CTA for the same 6 KB -- an L2
-                    // hot spot that made the normed phases' staging 1-2.5 us longer than the others'.)
-                    if (s == 0 && has_norm && warp >= 1 && warp <= 4) {
-                        const int total = op.ssq_in_parts * 8;
-                        float pr[12];
-#pragma unroll
-                        for (int q = 0; q < 12; ++q) {
-                            const int f = (warp - 1) * 32 + lane + 128 * q;
-                            pr[q] = f < total ? __ldcg(op.ssq_in + f) : 0.0f;
-                        }
+                    if (s == 0 && has_norm && warp < B) {
                         float ss = 0.0f;
+                        float pr[8];
 #pragma unroll
-                        for (int q = 0; q < 12; ++q) ss += pr[q];
-                        for (int f = (warp - 1) * 32 + lane + 128 * 12; f < total; f += 128) ss += __ldcg(op.ssq_in + f);
-                        ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-                        ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-                        if (lane < 8) rpart[(warp - 1) * 8 + lane] = ss;
+                        for (int q = 0; q < 8; ++q) {
+                            const int i = lane + 32 * q;
+                            pr[q] = i < op.ssq_in_parts ? __ldcg(op.ssq_in + (size_t)i * B + warp) : 0.0f;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) ss += pr[q];
+                        for (int i = lane + 256; i < op.ssq_in_parts; i += 32) ss += __ldcg(op.ssq_in + (size_t)i * B + warp);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                        if (lane == 0) rinv[warp] = 1.0f / sqrtf(ss / (float)K + p.eps);
                     }
-                    cbar();  // the warps' partial sums are visible
-                    // 1/rms per token: first read by the epilogue, i.e. behind the first tile group's CTA barrier
-                    if (s == 0 && has_norm && tid < B)
-                        rinv[tid] = 1.0f / sqrtf((((rpart[tid] + rpart[8 + tid]) + (rpart[16 + tid] + rpart[24 + tid]))) / (float)K + p.eps);
+                    mbar_wait(stg, stg_phase, wd_flag, 0x500u + (unsigned)oi);
+                    stg_phase ^= 1u;
+                    cbar();  // rinv visible to the epilogue threads
                     if (tracing && s == 0) p.trace[oi * 6 + 1] = (unsigned long long)clock64();
                     // the CTA's tiles NT at a time: every warp carries NT independent accumulation chains that
                     // share one read of the activation fragments
@@ -570,7 +563,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
 #ifdef VOX_MEGA_WARP_TRACE
                         // warp-level trace of the lm_head phase's first groups (CTA 0; debug "mega_trace_w")
                         unsigned long long *tw = nullptr;
-                        if (p.trace_w != nullptr && cta == 0 && lane == 0 && oi == (p.trace_w_op >= 0 ? p.trace_w_op : p.n_ops - 2) && s == 0 && it / NT < 6)
+                        if (p.trace_w != nullptr && cta == 0 && lane == 0 && oi == p.n_ops - 2 && s == 0 && it / NT < 6)
                             tw = p.trace_w + ((size_t)warp * 6 + it / NT) * 8;
                         if (tw) tw[0] = (unsigned long long)clock64();
 #else
@@ -581,10 +574,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         for (int u = 0; u < NT; ++u)
 #pragma unroll
                             for (int c = 0; c < 2 * CG; ++c) acc[u][c] = 0.0f;
-                        // reducer threads: the LAST RW warps (the SM's issue arbiter favours high warp ids: the short epilogue then
-                        // overtakes the other warps' next weight loop instead of starving behind it), indexed by rt:
-                        // (tile slot, token, row) = (rt / 16MT, (rt % 16MT) / 16, rt % 16)
-                        const int rt = tid - (MG_CWARPS - RW) * 32;  // < 0: not a reducer
+                        // reducer threads: RW of the 16 warps, a different set every group (round robin over the 16 / RW sets,
+                        // starting with the last warps).  The epilogue (~1000-1500 cycles: 16 partials per output, norm / bias /
+                        // residual, fragments for the next matvec) runs while the other warps are already in the next group's
+                        // weight loop; with a fixed set those warps did loop + epilogue every group and set the pace of every
+                        // ring stage (all 16 warps must release it).  Consecutive epilogues never overlap: the next group's CTA
+                        // barrier is behind this set's epilogue.  (flag 128: the last RW warps every group, as before.)
+                        // Indexed by rt: (tile slot, token, row) = (rt / 16MT, (rt % 16MT) / 16, rt % 16)
+                        const int rset_w = red_rotate ? (NSETS - 1 - (group_ctr % NSETS)) * RW : (MG_CWARPS - RW);
+                        ++group_ctr;
+                        const bool is_red = warp >= rset_w && warp < rset_w + RW;
+                        const int rt = is_red ? tid - rset_w * 32 : -1;  // < 0: not a reducer of this group
                         const int r_slot = rt / (16 * MT), r_tok = (rt % (16 * MT)) >> 4, r_r = rt & 15;
                         const int r_tile = mg_tile_of(it + r_slot, UT, cta, nctas);
                         const int r_row = r_tile * 16 + r_r;
@@ -600,11 +600,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         const int f_lb = UT <= NT ? it + bi * UT : it + NT - UT;  // list index of the block's first tile
                         const int f_blk = cta + (f_lb / UT) * nctas;              // unit index = block index
                         const bool bact = rt >= 0 && fout_bf != nullptr && s + 1 == S && bi < f_nblk && bm_ < B;
-                        float4 fg_lo = make_float4(1.f, 1.f, 1.f, 1.f), fg_hi = fg_lo;
-                        if (bact && fout_gamma) {
-                            fg_lo = *reinterpret_cast<const float4 *>(fout_gamma + (size_t)f_blk * 32 + 4 * bt);
-                            fg_hi = *reinterpret_cast<const float4 *>(fout_gamma + (size_t)f_blk * 32 + 16 + 4 * bt);
-                        }
                         // ---- the weight loop: one block pair per warp per ring stage, for the group's nt tiles.
                         // Guard-free bodies (nt is warp-uniform: one instantiation per count; a warp without a pair in
                         // a ragged last chunk only recycles the stage).
@@ -612,8 +607,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                             const uint32_t slot_q = (uint32_t)warp * 512u + (uint32_t)lane * 16u;
                             const uint32_t slot_d = (uint32_t)MG_SLOT_Q + (uint32_t)warp * 64u + (uint32_t)g * 8u;
                             for (int c0 = 0; c0 < np; c0 += MG_CHUNK) {
-                                // first pass over this K slice: the fragments of this chunk must have landed
-                                if (it == 0 && c0 % CP == 0) mbar_wait(&stgc[c0 / CP], stg_par, wd_flag, 0x500u + (unsigned)oi);
                                 mbar_wait(&full[stage], phase, wd_flag, 0x200u + (unsigned)oi);
                                 if (tracing && s == 0 && it == 0 && c0 == 0) p.trace[oi * 6 + 4] = (unsigned long long)clock64();
                                 if (tr_all && s == 0 && it == 0 && c0 == 0) ta[3] = (unsigned long long)clock64();
@@ -668,7 +661,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         }
                         cbar();
                         if (tw) tw[5] = (unsigned long long)clock64();
-                        if (warp >= MG_CWARPS - RW) {
+                        if (is_red) {
+                            // the consumer's norm weight for the builder's 8 elements: requested first, used last (not held across
+                            // the weight loop: 8 registers there cost spills, and spills are L2 round trips in this kernel)
+                            float4 fg_lo = make_float4(1.f, 1.f, 1.f, 1.f), fg_hi = fg_lo;
+                            if (bact && fout_gamma) {
+                                fg_lo = *reinterpret_cast<const float4 *>(fout_gamma + (size_t)f_blk * 32 + 4 * bt);
+                                fg_hi = *reinterpret_cast<const float4 *>(fout_gamma + (size_t)f_blk * 32 + 16 + 4 * bt);
+                            }
                             float v = 0.0f;
                             if (r_valid) {
                                 const float *rp = red + (size_t)par * MG_CWARPS * (NT * 16 * MT) + rt;
@@ -681,7 +681,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
 #pragma unroll
                                     for (int w = 0; w < MG_CWARPS; w += 2 * st) pw[w] += pw[w + st];
                                 v = pw[0];
-                                if (tw) tw[7] = (unsigned long long)clock64();
                                 if (S > 1) {
                                     float *at = acc_tile + (size_t)(it + r_slot) * 16 * MT + (rt % (16 * MT));
                                     if (s > 0) v += *at;
@@ -714,7 +713,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                                         sq += __shfl_xor_sync(0xffffffffu, sq, 4);
                                         sq += __shfl_xor_sync(0xffffffffu, sq, 2);
                                         sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                                        if (live && r_r == 0) ssq_out[(size_t)r_tile * 8 + r_tok] = sq;
+                                        if (live && r_r == 0) ssq_out[(size_t)r_tile * B + r_tok] = sq;
                                     }
                                 }
                                 if (fout_bf) {
@@ -753,10 +752,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 }
             }
             if (fout_bf) asm volatile("fence.proxy.async;\n" ::: "memory");  // fragments are read by bulk copies next phase
-            if (track && warp >= MG_CWARPS - RW) {
-                const int rt = tid - (MG_CWARPS - RW) * 32;
-                // this CTA's best candidate per stream (lowest index wins ties: order independent):
-                // first the 16 rows of a (slot, token) group, then the NT slots through shared memory
+            if (track) {
+                // this CTA's best candidate per stream (lowest index wins ties: order independent).  Every warp may have been
+                // a reducer (rotating sets); a thread's (tile slot, token) is the same in every group it reduced:
+                // first the 16 rows of a (slot, token) group, then the sets and slots through shared memory
+                const int rta = tid % (RW * 32), rset = warp / RW;
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) {
                     const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
@@ -764,25 +764,21 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                     amax_combine(best_v, best_i, ov, ox);
                 }
                 // `vals` is idle in this op (only fragment-producing ops use it) -- not `red`, which slower epilogue
-                // warps may still be reading: [NT][MT] values, then [NT][MT] indices
+                // warps may still be reading: [NSETS][NT][MT] values, then as many indices
                 float *cv = vals;
-                int *ci = reinterpret_cast<int *>(vals + NT * MT);
-                if ((rt & 15) == 0 && rt < NT * 16 * MT) {
-                    cv[rt >> 4] = best_v;
-                    ci[rt >> 4] = best_i;
+                int *ci = reinterpret_cast<int *>(vals + NSETS * NT * MT);
+                if ((rta & 15) == 0 && rta < NT * 16 * MT) {
+                    cv[rset * (NT * MT) + (rta >> 4)] = best_v;
+                    ci[rset * (NT * MT) + (rta >> 4)] = best_i;
                 }
                 best_v = -INFINITY;
                 best_i = 0x7fffffff;
-            }
-            if (track) {
                 cbar();
                 if (tid < B) {
                     float bv = -INFINITY;
                     int bx = 0x7fffffff;
-                    const float *cv = vals;
-                    const int *ci = reinterpret_cast<const int *>(vals + NT * MT);
 #pragma unroll
-                    for (int u = 0; u < NT; ++u) amax_combine(bv, bx, cv[u * MT + tid], ci[u * MT + tid]);
+                    for (int u = 0; u < NSETS * NT; ++u) amax_combine(bv, bx, cv[u * MT + tid], ci[u * MT + tid]);
                     p.am_vals[(size_t)cta * 8 + tid] = bv;
                     p.am_idx[(size_t)cta * 8 + tid] = bx;
                 }
@@ -805,51 +801,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             for (int unit = cta; unit < B * Hkv * NC; unit += nctas) {
                 const int ch = unit % NC, bk = unit / NC;
                 const int b = bk / Hkv, kvh = bk - b * Hkv;
-                const int pos = s_pos[b];                // per row: sessions of different ages share the step
+                const int pos = p.d_pos[b];              // per row: sessions of different ages share the step
                 if (pos >= max_seq) continue;
                 const int j_lo = pos - p.window > 0 ? pos - p.window : 0;
                 const int per = (pos - j_lo + NC) / NC;  // ceil((pos - j_lo + 1) / NC) keys per chunk
                 const int j0 = j_lo + ch * per, j1 = min(pos + 1, j0 + per);  // keys [j0, j1)
                 const bool has_new = j0 <= pos && pos < j1;                    // this chunk holds the new row
                 const float *row = p.qkv + (size_t)b * p.ld_qkv;
-                const bool pt_s = pt_cached && unit == cta;  // the unit's page-table row is in shared memory
-                auto kv_at = [&](const int j) -> size_t {
-                    const int phys = pt_s ? s_pt[j / KV_PAGE] : kvw.page_table[(size_t)b * kvw.max_pages + (j / KV_PAGE)];
-                    return (((size_t)phys * Hkv + kvh) * KV_PAGE + (j % KV_PAGE)) * HD;
-                };
-                constexpr int KU = 4;  // keys in flight per warp; one softmax rescale per KU keys
-                float kk[KU][DPL], vv[KU][DPL];
-                // keys jb + u * 16 (u < KU) of the cache -> registers; the row being appended (j == pos) is patched in from
-                // shared memory by the caller
-                auto load_keys = [&](const int jb) {
-#pragma unroll
-                    for (int u = 0; u < KU; ++u) {
-                        const int j = jb + u * MG_CWARPS;
-                        if (j < j1 && j != pos) {
-                            const size_t at = kv_at(j) + lane * DPL;
-                            const float *kr = kvw.k + at;
-                            const float *vr = kvw.v + at;
-                            if constexpr (DPL == 4) {
-                                const float4 k4 = *reinterpret_cast<const float4 *>(kr);
-                                const float4 v4 = *reinterpret_cast<const float4 *>(vr);
-                                kk[u][0] = k4.x; kk[u][1] = k4.y; kk[u][2] = k4.z; kk[u][3] = k4.w;
-                                vv[u][0] = v4.x; vv[u][1] = v4.y; vv[u][2] = v4.z; vv[u][3] = v4.w;
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < DPL; ++i) {
-                                    kk[u][i] = kr[i];
-                                    vv[u][i] = vr[i];
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < DPL; ++i) kk[u][i] = vv[u][i] = 0.0f;
-                        }
-                    }
-                };
-                // the first batch of keys is requested BEFORE q, k, v of the new row are staged: the two round trips overlap
-                const bool kv_early = !(p.flags & 64);   // flag 64: experiment -- request them after the staging instead
-                if (kv_early && j0 + warp < j1) load_keys(j0 + warp);
                 cbar();  // scratch free (previous unit / previous op)
                 // q (G heads) and k through RoPE on the way in (rope.rs:103-141: interleaved pairs), v as is
                 constexpr int half = HD / 2;
@@ -867,7 +825,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 if (tracing) p.trace[oi * 6 + 1] = (unsigned long long)clock64();
                 if (tr_all) ta[3] = (unsigned long long)clock64();
                 if (has_new) {
-                    const size_t at = kv_at(pos);
+                    const size_t at = kv_index(kvw, b, Hkv, kvh, pos, HD);
                     for (int i = tid; i < HD; i += MG_CTHREADS) {
                         kvw.k[at + i] = kvs[i];
                         kvw.v[at + i] = kvs[HD + i];
@@ -886,11 +844,29 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
 #pragma unroll
                     for (int i = 0; i < DPL; ++i) acc[h][i] = 0.0f;
                 }
+                constexpr int KU = 4;  // keys in flight per warp; one softmax rescale per KU keys
                 for (int jb = j0 + warp; jb < j1; jb += KU * MG_CWARPS) {
-                    if (!kv_early || jb != j0 + warp) load_keys(jb);
+                    float kk[KU][DPL], vv[KU][DPL];
 #pragma unroll
                     for (int u = 0; u < KU; ++u) {
-                        if (jb + u * MG_CWARPS == pos) {  // the row appended above, still in shared memory
+                        const int j = jb + u * MG_CWARPS;
+                        if (j < j1 && j != pos) {
+                            const size_t at = kv_index(kvw, b, Hkv, kvh, j, HD) + lane * DPL;
+                            const float *kr = kvw.k + at;
+                            const float *vr = kvw.v + at;
+                            if constexpr (DPL == 4) {
+                                const float4 k4 = *reinterpret_cast<const float4 *>(kr);
+                                const float4 v4 = *reinterpret_cast<const float4 *>(vr);
+                                kk[u][0] = k4.x; kk[u][1] = k4.y; kk[u][2] = k4.z; kk[u][3] = k4.w;
+                                vv[u][0] = v4.x; vv[u][1] = v4.y; vv[u][2] = v4.z; vv[u][3] = v4.w;
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < DPL; ++i) {
+                                    kk[u][i] = kr[i];
+                                    vv[u][i] = vr[i];
+                                }
+                            }
+                        } else {  // j == pos: the row appended above, still in shared memory (j >= j1: unused)
 #pragma unroll
                             for (int i = 0; i < DPL; ++i) {
                                 kk[u][i] = kvs[lane * DPL + i];
@@ -1079,8 +1055,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         sh += __shfl_xor_sync(0xffffffffu, sh, o);
                     }
                     if (act && j == 0) {
-                        p.ssq_x[(size_t)(2 * blk) * 8 + b] = sl;
-                        p.ssq_x[(size_t)(2 * blk + 1) * 8 + b] = sh;
+                        p.ssq_x[(size_t)(2 * blk) * B + b] = sl;
+                        p.ssq_x[(size_t)(2 * blk + 1) * B + b] = sh;
                     }
                 }
                 cbar();

@@ -99,7 +99,7 @@ struct MegaParams {
     // experiment switches (VOX_MEGA_FLAGS): 1 no evict-first hint, 2 no KV-cache L2 prefetch, 4 no norm-weight prefetch,
     // 8 fragments copied in one piece (no per-CTA rotation), 16 weight loop without the arithmetic (garbage results:
     // measures the memory pipeline alone), 32 ring stages released after the arithmetic (instead of right after the
-    // warp's loads of the stage), 64 attention K/V loads issued after (not before) the staging of q, k, v
+    // warp's loads of the stage)
     int flags = 0;
     float *logits_out = nullptr;  // != nullptr: where the lm_head op writes its rows (row groups of a larger batch)
 };
