@@ -51,8 +51,14 @@ constexpr int MG_CTHREADS = MG_CWARPS * 32;
 // registers to the consumers (setmaxnreg works on whole warpgroups of 4 warps).  The register file is allocated in units of
 // 4 warps anyway: 17 warps cost as many registers as 20.
 constexpr int MG_THREADS = MG_CTHREADS + 128;
-constexpr int MG_REGS_CONSUMER = 112;            // 16 x 32 x (112 - 96) = 8192 registers moved ...
-constexpr int MG_REGS_PRODUCER = 32;             // ... from the producer's warpgroup: 4 x 32 x (96 - 32) = 8192
+constexpr int MG_REGS_CONSUMER = 104;            // 16 x 32 x (104 - 96) = 4096 registers moved ...
+constexpr int MG_REGS_PRODUCER = 64;             // ... from the producer / epilogue warpgroup: 4 x 32 x (96 - 64) = 4096
+constexpr int MG_EWARPS = 3;                     // epilogue warps (17..19)
+constexpr int MG_ETHREADS = MG_EWARPS * 32;
+constexpr int MG_ATHREADS = MG_CTHREADS + MG_ETHREADS;  // consumers + epilogue warps (the producer joins no barrier)
+// named barriers: 1 consumers (512), 2 epilogue warps (96), 3 consumers + epilogue warps (phase ends), 4/5 partial sums of
+// the group in red[0/1] complete (consumers arrive, epilogue warps wait), 6/7 red[0/1] read (the other way round)
+constexpr int MG_BAR_FULL = 4, MG_BAR_FREE = 6;
 constexpr int MG_CHUNK = 16;                     // block pairs per ring stage (one per consumer warp)
 constexpr int MG_SLOT_Q = MG_CHUNK * 512;        // nibble bytes of one tile's part of a stage; its scales follow
 constexpr int MG_SLOT_BYTES = MG_CHUNK * 576;    // a stage holds NT such slots (NT tiles advance together)
@@ -71,7 +77,7 @@ static_assert(mg_vals(1) >= 2 * mg_nt(1) * 1 && mg_vals(2) >= 2 * mg_nt(2) * 2 &
               "vals also holds the lm_head phase's per-slot argmax candidates");
 // barriers + rinv + red[2][16 warps][NT*16*MT] + acc_tile[MG_ACC_TILES][16*MT] + vals
 __host__ __device__ constexpr int mg_misc_bytes(int MT) {
-    return ((432 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT + 4 * mg_vals(MT)) + 127) & ~127;
+    return ((432 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT + 4 * mg_vals(MT) + 256) + 127) & ~127;  // + s_op
 }
 __host__ __device__ constexpr int mg_pair_bytes(int MT) { return 272 * MT; }  // fragments + offsets of one block pair
 
@@ -158,6 +164,19 @@ __device__ __forceinline__ void rbar() {
 }
 // barrier among the 512 consumer threads (the producer warp never joins)
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+// barrier among the epilogue warps
+__device__ __forceinline__ void ebar() { asm volatile("bar.sync 2, %0;\n" ::"n"(MG_ETHREADS) : "memory"); }
+// consumers + epilogue warps
+__device__ __forceinline__ void abar() { asm volatile("bar.sync 3, %0;\n" ::"n"(MG_ATHREADS) : "memory"); }
+// producer/consumer hand-off on barrier `id` (MG_ATHREADS participants: one side arrives, the other waits)
+// (`publish`: the arriving thread's shared-memory stores must be visible to the waiting side.  Not __threadfence_block():
+// that compiles to MEMBAR.SC, which on the epilogue warps waited for their outstanding GLOBAL stores -- an L2 round trip per
+// tile group.)
+__device__ __forceinline__ void hbar_arrive(const int id, const bool publish) {
+    if (publish) asm volatile("fence.acq_rel.cta;\n" ::: "memory");
+    asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "n"(MG_ATHREADS) : "memory");
+}
+__device__ __forceinline__ void hbar_sync(const int id) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "n"(MG_ATHREADS) : "memory"); }
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t a0, const uint32_t a1, const uint32_t a2,
                                          const uint32_t a3, const uint32_t b0, const uint32_t b1) {
@@ -353,8 +372,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     static_assert(G * HD <= MG_CTHREADS, "one attention output per consumer thread");
     constexpr int NT = mg_nt(MT);
     constexpr int RW = (NT * 16 * MT + 31) / 32;  // warps that add the per-warp partial sums and run the epilogue
-    constexpr int NSETS = MG_CWARPS / RW;         // reducer sets (the role rotates from group to group)
-    static_assert(MG_CWARPS % RW == 0 && 2 * NSETS * NT * MT <= mg_vals(MT), "reducer sets tile the consumer warps; vals holds their argmax candidates");
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + MG_MAX_STAGES;
@@ -362,6 +379,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     float *red = rinv + 8;                                            // [2][MG_CWARPS][NT*16*MT]
     float *acc_tile = red + 2 * MG_CWARPS * NT * 16 * MT;             // [MG_ACC_TILES][16*MT]
     float *vals = acc_tile + MG_ACC_TILES * 16 * MT;                  // [1 or 2 blocks][32][MT]
+    MegaOp *s_op = reinterpret_cast<MegaOp *>(vals + mg_vals(MT));  // the current op's descriptor for the epilogue warps
+    static_assert(sizeof(MegaOp) <= 256 && sizeof(MegaOp) % 4 == 0, "s_op");
     uint64_t *stg = empty + MG_MAX_STAGES;                            // activation fragments landed in scratch
     unsigned char *scratch = smem + mg_misc_bytes(MT);
     unsigned char *ring = scratch + p.scratch_bytes;
@@ -440,6 +459,255 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                     }
                 }
             }
+        } else if (warp > MG_CWARPS) {
+            // =========================== epilogue warps ===========================
+            // The 16 consumer warps leave their partial sums of a tile group in red[par] and go straight on to the next
+            // group's weight stream; the epilogue warps add the 16 partials per output in fixed (tree) order and run the
+            // epilogue (norm / bias / residual / SiLU*up / running argmax / fragments for the next matvec).
+            // These warps share the SM's issue slots with 16 busy consumer warps (they get ~1/5 of a sub-partition), so the
+            // role is written for instruction count: thread e owns FOUR consecutive rows of one (tile slot, token) --
+            // outputs rt = 4e .. 4e+3 of the group, (slot, token, row) = (rt / 16MT, (rt % 16MT) / 16, rt % 16) -- i.e. one
+            // 128-bit load per partial, one 128-bit residual load and one 128-bit store; a first version with one output per
+            // thread and three passes (~1070 instructions per group and warp) could not keep up with the consumers.
+            constexpr int NOUT = NT * 16 * MT;
+            constexpr int NQ = NOUT / 4;                      // active epilogue threads (64 at 8 tokens)
+            static_assert(NQ <= MG_ETHREADS && NOUT % 4 == 0, "one quad of rows per epilogue thread");
+            const int e = tid - (MG_CTHREADS + 32);
+            const bool qact = e < NQ;
+            const int q_slot = (4 * e) / (16 * MT), q_tok = ((4 * e) % (16 * MT)) >> 4, q_r0 = (4 * e) & 15;
+            int par = 0;
+            float best_v = -INFINITY;
+            int best_i = 0x7fffffff;
+            for (int oi = 0; oi < p.n_ops; ++oi) {
+                const MegaOp &op = p.ops[oi];
+                if (op.kind == MG_MATVEC) {
+                    const int n_tiles = op.n_tiles, S = op.S, N = op.N;
+                    const int epi = op.epi, ldy = op.ldy, track = op.track_argmax, UT = op.unit_tiles;
+                    const int ush = UT == 4 ? 2 : (UT == 2 ? 1 : 0);   // unit_tiles is 1, 2 or 4 (host-checked)
+                    const bool has_norm = op.gamma != nullptr;
+                    // The descriptor's pointers are needed a few times per group: they live in shared memory (an LDS at the
+                    // point of use), not in registers -- this role runs on 64 registers, and spills are expensive here.
+                    {
+                        const uint32_t *src = reinterpret_cast<const uint32_t *>(&op);
+                        uint32_t *dst = reinterpret_cast<uint32_t *>(s_op);
+                        if (e < (int)(sizeof(MegaOp) / 4)) dst[e] = src[e];
+                        ebar();
+                    }
+                    const volatile MegaOp *const vop = s_op;
+#define yout ((track && p.logits_out) ? p.logits_out : vop->y)
+#define bias (vop->bias)
+#define resid (vop->res)
+#define ssq_out (vop->ssq_out)
+#define fout_bf (vop->fout_bf)
+#define fout_off (vop->fout_off)
+#define fout_gamma (vop->fout_gamma)
+                    const int ntl = mg_tile_count(n_tiles, UT, cta, nctas);
+                    const bool vec_ok = ((ldy | N) & 3) == 0;   // 128-bit residual loads / output stores are aligned
+                    // fragment builders: thread e = (block within the group, token, t)
+                    const int bi = e / (4 * MT), bm_ = (e % (4 * MT)) >> 2, bt = e & 3;
+                    for (int s = 0; s < S && ntl > 0; ++s) {
+                        const bool last = s + 1 == S;
+                        for (int it = 0; it < ntl; it += NT) {
+                            const int nt = min(NT, ntl - it);
+                            const int li = it + q_slot;                                   // index in the CTA's tile list
+                            const int r_tile = ((cta + (li >> ush) * nctas) << ush) + (li & (UT - 1));
+                            const int r_row = r_tile * 16 + q_r0;
+                            const bool r_valid = qact && q_slot < nt;
+                            const bool live = r_valid && q_tok < B;
+                            // the epilogue's residual operand and the builder's norm weight: L2 round trips, started while
+                            // the consumers are still streaming the group
+                            float4 res4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            const bool quad_in = r_row + 3 < N;   // (else: a ragged last tile, handled row by row)
+                            if (epi == EPI_RESIDUAL && last && live) {
+                                const float *rsrc = resid + (size_t)q_tok * ldy + r_row;
+                                if (vec_ok && quad_in) {
+                                    res4 = __ldcg(reinterpret_cast<const float4 *>(rsrc));
+                                } else {
+                                    if (r_row + 0 < N) res4.x = __ldcg(rsrc + 0);
+                                    if (r_row + 1 < N) res4.y = __ldcg(rsrc + 1);
+                                    if (r_row + 2 < N) res4.z = __ldcg(rsrc + 2);
+                                    if (r_row + 3 < N) res4.w = __ldcg(rsrc + 3);
+                                }
+                            }
+                            const int f_nblk = UT <= NT ? nt / UT : (((it + NT) % UT == 0) ? 1 : 0);
+                            const int f_lb = UT <= NT ? it + bi * UT : it + NT - UT;  // list index of the block's first tile
+                            const int f_blk = cta + (f_lb >> ush) * nctas;            // unit index = block index
+                            const bool bact = fout_bf != nullptr && last && bi < f_nblk && bm_ < B;
+                            float4 fg_lo = make_float4(1.f, 1.f, 1.f, 1.f), fg_hi = fg_lo;
+                            if (bact && fout_gamma) {
+                                const float4 *gq4 = reinterpret_cast<const float4 *>(fout_gamma + (size_t)f_blk * 32);
+                                fg_lo = gq4[bt];
+                                fg_hi = gq4[4 + bt];
+                            }
+                            hbar_sync(MG_BAR_FULL + par);   // the 16 warps' partial sums of this group are in red[par]
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (r_valid) {
+                                // fixed-shape tree over the 16 warps' partials (((0+1)+(2+3))+((4+5)+(6+7)))+(...), four loads at a time
+                                const float4 *rp = reinterpret_cast<const float4 *>(red + (size_t)par * MG_CWARPS * NOUT) + e;
+                                auto add4 = [](const float4 a, const float4 c) { return make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w); };
+                                float4 oct[2];
+#pragma unroll
+                                for (int o = 0; o < 2; ++o) {
+                                    float4 quad[2];
+#pragma unroll
+                                    for (int qd = 0; qd < 2; ++qd) {
+                                        const int w0 = o * 8 + qd * 4;
+                                        const float4 p0 = rp[(w0 + 0) * (NOUT / 4)], p1 = rp[(w0 + 1) * (NOUT / 4)];
+                                        const float4 p2 = rp[(w0 + 2) * (NOUT / 4)], p3 = rp[(w0 + 3) * (NOUT / 4)];
+                                        quad[qd] = add4(add4(p0, p1), add4(p2, p3));
+                                    }
+                                    oct[o] = add4(quad[0], quad[1]);
+                                }
+                                v = add4(oct[0], oct[1]);
+                                if (S > 1) {
+                                    float4 *at = reinterpret_cast<float4 *>(acc_tile + (size_t)li * 16 * MT) + (e % (4 * MT));
+                                    if (s > 0) v = add4(v, *at);
+                                    if (!last) *at = v;
+                                }
+                            }
+                            if (last) {
+                                if (has_norm && live) {
+                                    const float ri = rinv[q_tok];
+                                    v.x *= ri; v.y *= ri; v.z *= ri; v.w *= ri;
+                                }
+                                const int be = UT <= NT ? q_slot / UT : 0;        // block within this group
+                                const int ti = li & (UT - 1);                     // tile within its unit
+                                if (fout_bf) ebar();  // the previous group's builders are done with vals
+                                if (epi == EPI_SILU_MUL) {
+                                    // rows (2i, 2i+1) = (gate, up) of output i: both pairs of this quad are in this thread
+                                    if (live && r_row + 3 < N) {
+                                        const float f0 = (v.x / (1.0f + expf(-v.x))) * v.y, f1 = (v.z / (1.0f + expf(-v.z))) * v.w;
+                                        if (yout) {
+                                            yout[(size_t)q_tok * ldy + (r_row >> 1)] = f0;
+                                            yout[(size_t)q_tok * ldy + (r_row >> 1) + 1] = f1;
+                                        }
+                                        if (fout_bf) {
+                                            float *vd = vals + (size_t)(be * 32 + ti * 8 + (q_r0 >> 1)) * MT + q_tok;
+                                            vd[0] = f0;
+                                            vd[MT] = f1;
+                                        }
+                                    }
+                                } else {
+                                    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (live && r_row < N) {
+                                        out = v;
+                                        if (!quad_in) {   // rows beyond N contribute nothing (statistics, fragments, argmax)
+                                            if (r_row + 1 >= N) out.y = 0.0f;
+                                            if (r_row + 2 >= N) out.z = 0.0f;
+                                            out.w = 0.0f;
+                                        }
+                                        if (bias) {
+                                            out.x += bias[r_row];
+                                            if (r_row + 1 < N) out.y += bias[r_row + 1];
+                                            if (r_row + 2 < N) out.z += bias[r_row + 2];
+                                            if (r_row + 3 < N) out.w += bias[r_row + 3];
+                                        }
+                                        if (epi == EPI_RESIDUAL) { out.x += res4.x; out.y += res4.y; out.z += res4.z; out.w += res4.w; }
+                                        if (epi == EPI_GELU) {
+                                            out.x = 0.5f * out.x * (1.0f + erff(out.x * 0.70710678118654752440f));
+                                            out.y = 0.5f * out.y * (1.0f + erff(out.y * 0.70710678118654752440f));
+                                            out.z = 0.5f * out.z * (1.0f + erff(out.z * 0.70710678118654752440f));
+                                            out.w = 0.5f * out.w * (1.0f + erff(out.w * 0.70710678118654752440f));
+                                        }
+                                        if (yout) {
+                                            float *yd = yout + (size_t)q_tok * ldy + r_row;
+                                            if (vec_ok && quad_in) {
+                                                *reinterpret_cast<float4 *>(yd) = out;
+                                            } else {
+                                                yd[0] = out.x;
+                                                if (r_row + 1 < N) yd[1] = out.y;
+                                                if (r_row + 2 < N) yd[2] = out.z;
+                                                if (r_row + 3 < N) yd[3] = out.w;
+                                            }
+                                        }
+                                        if (track) {   // ascending rows: the lowest index wins ties
+                                            amax_combine(best_v, best_i, out.x, r_row);
+                                            if (r_row + 1 < N) amax_combine(best_v, best_i, out.y, r_row + 1);
+                                            if (r_row + 2 < N) amax_combine(best_v, best_i, out.z, r_row + 2);
+                                            if (r_row + 3 < N) amax_combine(best_v, best_i, out.w, r_row + 3);
+                                        }
+                                        if (fout_bf) {
+                                            float *vd = vals + (size_t)(be * 32 + ti * 16 + q_r0) * MT + q_tok;
+                                            vd[0] = out.x;
+                                            vd[MT] = out.y;
+                                            vd[2 * MT] = out.z;
+                                            vd[3 * MT] = out.w;
+                                        }
+                                    }
+                                    if (ssq_out) {   // sum of squares of the tile's 16 rows: 4 in this thread, 4 lanes per tile
+                                        float sq = (out.x * out.x + out.y * out.y) + (out.z * out.z + out.w * out.w);
+                                        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                                        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                                        if (live && q_r0 == 0) ssq_out[(size_t)r_tile * B + q_tok] = sq;
+                                    }
+                                }
+                                if (fout_bf) {
+                                    // ---- this group's outputs become the next matvec's activation fragments:
+                                    // a unit of UT consecutive tiles = one 32-value block per token
+                                    ebar();
+                                    if (e < ((2 * 4 * MT + 31) / 32) * 32) {  // warp-uniform: the warps holding builder lanes
+                                        float4 l = make_float4(0.f, 0.f, 0.f, 0.f), h = l;
+                                        if (bact) {
+                                            const float *vb = vals + (size_t)(bi * 32) * MT + bm_;
+                                            l = make_float4(vb[(4 * bt + 0) * MT], vb[(4 * bt + 1) * MT], vb[(4 * bt + 2) * MT], vb[(4 * bt + 3) * MT]);
+                                            h = make_float4(vb[(16 + 4 * bt + 0) * MT], vb[(16 + 4 * bt + 1) * MT], vb[(16 + 4 * bt + 2) * MT],
+                                                            vb[(16 + 4 * bt + 3) * MT]);
+                                            l = mul4(l, fg_lo);
+                                            h = mul4(h, fg_hi);
+                                        }
+                                        frag_build<MT>(l, h, bact, bt, bm_, fout_bf + (size_t)f_blk * (16 * MT), fout_off + (size_t)f_blk * MT);
+                                    }
+                                }
+                            }
+                            // red[par] has been read (the partials were consumed by the sums above; the stores that depend
+                            // on them have been issued): the consumers may overwrite it two groups from now
+                            hbar_arrive(MG_BAR_FREE + par, false);
+                            par ^= 1;
+                        }
+                    }
+                    if (fout_bf) asm volatile("fence.proxy.async;\n" ::: "memory");  // fragments are read by bulk copies next phase
+                    if (track) {
+                        // this CTA's best candidate per stream (lowest index wins ties: order independent):
+                        // first the 4 quads (16 rows) of a (slot, token) group, then the NT slots through shared memory
+                        float *cv = vals;   // idle in this op (only fragment-producing ops use it): [NT][MT] values, then indices
+                        int *ci = reinterpret_cast<int *>(vals + NT * MT);
+#pragma unroll
+                        for (int o = 2; o > 0; o >>= 1) {
+                            const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+                            const int ox = __shfl_xor_sync(0xffffffffu, best_i, o);
+                            amax_combine(best_v, best_i, ov, ox);
+                        }
+                        if (qact && (e & 3) == 0) {
+                            cv[e >> 2] = best_v;     // = slot * MT + token
+                            ci[e >> 2] = best_i;
+                        }
+                        best_v = -INFINITY;
+                        best_i = 0x7fffffff;
+                        ebar();
+                        if (e < B) {
+                            float bv = -INFINITY;
+                            int bx = 0x7fffffff;
+#pragma unroll
+                            for (int u = 0; u < NT; ++u) amax_combine(bv, bx, cv[u * MT + e], ci[u * MT + e]);
+                            p.am_vals[(size_t)cta * 8 + e] = bv;
+                            p.am_idx[(size_t)cta * 8 + e] = bx;
+                        }
+                    }
+#undef yout
+#undef bias
+#undef resid
+#undef ssq_out
+#undef fout_bf
+#undef fout_off
+#undef fout_gamma
+                }
+                // phase end: (1) everything this CTA wrote is ordered before thread 0's arrival at the grid barrier,
+                // (2) the next phase starts for all roles once thread 0 has seen every CTA arrive
+                if (oi + 1 < p.n_ops) {
+                    abar();
+                    abar();
+                }
+            }
         }
         return;
     }
@@ -449,13 +717,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     const int epoch = *p.d_epoch;  // decode steps run by this session so far (attention chunk flags)
     int stage = 0;
     uint32_t phase = 0, stg_phase = 0;
-    const bool red_rotate = !(p.flags & 128);  // flag 128: experiment -- the last RW warps reduce every group (old behaviour)
-    int group_ctr = 0;
     const bool early_release = !(p.flags & 32);  // flag 32: experiment -- release a stage after the arithmetic
-    int par = 0;
+    int par = 0, group_ctr = 0;
     unsigned bar_target = 0;
-    float best_v = -INFINITY;
-    int best_i = 0x7fffffff;
 
     for (int oi = 0; oi < p.n_ops; ++oi) {
         const MegaOp &op = p.ops[oi];
@@ -499,15 +763,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                     }
                 }
             }
-            const int n_tiles = op.n_tiles, n_pairs = op.n_pairs, S = op.S, Ps = op.Ps, N = op.N, K = op.K;
-            const int epi = op.epi, ldy = op.ldy, track = op.track_argmax, UT = op.unit_tiles;
+            const int n_tiles = op.n_tiles, n_pairs = op.n_pairs, S = op.S, Ps = op.Ps, K = op.K;
+            const int UT = op.unit_tiles;
             const bool has_norm = op.gamma != nullptr;
-            float *const yout = (op.track_argmax && p.logits_out) ? p.logits_out : op.y;
-            const float *const bias = op.bias, *const resid = op.res;
-            float *const ssq_out = op.ssq_out;
-            uint2 *const fout_bf = op.fout_bf;
-            float2 *const fout_off = op.fout_off;
-            const float *const fout_gamma = op.fout_gamma;
             const int ntl = mg_tile_count(n_tiles, UT, cta, nctas);
             float2 *off2 = reinterpret_cast<float2 *>(scratch);             // [2*Ps][MT]
             uint2 *bf = reinterpret_cast<uint2 *>(off2 + (size_t)Ps * 2 * MT);  // [2*Ps][2][2*MT][4]
@@ -574,32 +832,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         for (int u = 0; u < NT; ++u)
 #pragma unroll
                             for (int c = 0; c < 2 * CG; ++c) acc[u][c] = 0.0f;
-                        // reducer threads: RW of the 16 warps, a different set every group (round robin over the 16 / RW sets,
-                        // starting with the last warps).  The epilogue (~1000-1500 cycles: 16 partials per output, norm / bias /
-                        // residual, fragments for the next matvec) runs while the other warps are already in the next group's
-                        // weight loop; with a fixed set those warps did loop + epilogue every group and set the pace of every
-                        // ring stage (all 16 warps must release it).  Consecutive epilogues never overlap: the next group's CTA
-                        // barrier is behind this set's epilogue.  (flag 128: the last RW warps every group, as before.)
-                        // Indexed by rt: (tile slot, token, row) = (rt / 16MT, (rt % 16MT) / 16, rt % 16)
-                        const int rset_w = red_rotate ? (NSETS - 1 - (group_ctr % NSETS)) * RW : (MG_CWARPS - RW);
-                        ++group_ctr;
-                        const bool is_red = warp >= rset_w && warp < rset_w + RW;
-                        const int rt = is_red ? tid - rset_w * 32 : -1;  // < 0: not a reducer of this group
-                        const int r_slot = rt / (16 * MT), r_tok = (rt % (16 * MT)) >> 4, r_r = rt & 15;
-                        const int r_tile = mg_tile_of(it + r_slot, UT, cta, nctas);
-                        const int r_row = r_tile * 16 + r_r;
-                        const bool r_valid = rt >= 0 && rt < NT * 16 * MT && r_slot < nt;
-                        // the epilogue's residual operand: fetched now, used after the tile's weight stream
-                        float res_pre = 0.0f;
-                        if (epi == EPI_RESIDUAL && s + 1 == S && r_valid && r_tok < B && r_row < N)
-                            res_pre = __ldcg(resid + (size_t)r_tok * ldy + r_row);
-                        // fragment builders: (block within this group, token, t); the consumer's norm weight for
-                        // the builder's 8 elements is fetched now as well
-                        const int bi = rt / (4 * MT), bm_ = (rt % (4 * MT)) >> 2, bt = rt & 3;
-                        const int f_nblk = UT <= NT ? nt / UT : (((it + NT) % UT == 0) ? 1 : 0);
-                        const int f_lb = UT <= NT ? it + bi * UT : it + NT - UT;  // list index of the block's first tile
-                        const int f_blk = cta + (f_lb / UT) * nctas;              // unit index = block index
-                        const bool bact = rt >= 0 && fout_bf != nullptr && s + 1 == S && bi < f_nblk && bm_ < B;
                         // ---- the weight loop: one block pair per warp per ring stage, for the group's nt tiles.
                         // Guard-free bodies (nt is warp-uniform: one instantiation per count; a warp without a pair in
                         // a ragged last chunk only recycles the stage).
@@ -637,7 +869,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         }
                         if (tracing && s + 1 == S && it + NT >= ntl) p.trace[oi * 6 + 5] = (unsigned long long)clock64();
                         if (tw) tw[4] = (unsigned long long)clock64();
-                        // ---- the 16 warps' partial sums of these tiles meet in shared memory
+                        // ---- the 16 warps' partial sums of these tiles meet in shared memory: red[par] is handed to the epilogue
+                        // warps (they read it, run the epilogue, and give it back two groups later); this warp goes straight on
+                        // to the next group's weight stream
+                        if (group_ctr >= 2) hbar_sync(MG_BAR_FREE + par);   // the buffer's previous contents have been read
                         float *rw = red + (size_t)(par * MG_CWARPS + warp) * (NT * 16 * MT);
 #pragma unroll
                         for (int u = 0; u < NT; ++u) {
@@ -659,128 +894,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                                 }
                             }
                         }
-                        cbar();
+                        hbar_arrive(MG_BAR_FULL + par, true);
                         if (tw) tw[5] = (unsigned long long)clock64();
-                        if (is_red) {
-                            // the consumer's norm weight for the builder's 8 elements: requested first, used last (not held across
-                            // the weight loop: 8 registers there cost spills, and spills are L2 round trips in this kernel)
-                            float4 fg_lo = make_float4(1.f, 1.f, 1.f, 1.f), fg_hi = fg_lo;
-                            if (bact && fout_gamma) {
-                                fg_lo = *reinterpret_cast<const float4 *>(fout_gamma + (size_t)f_blk * 32 + 4 * bt);
-                                fg_hi = *reinterpret_cast<const float4 *>(fout_gamma + (size_t)f_blk * 32 + 16 + 4 * bt);
-                            }
-                            float v = 0.0f;
-                            if (r_valid) {
-                                const float *rp = red + (size_t)par * MG_CWARPS * (NT * 16 * MT) + rt;
-                                // fixed-shape tree over the 16 warps' partials: all loads in flight at once, depth-4 adds
-                                float pw[MG_CWARPS];
-#pragma unroll
-                                for (int w = 0; w < MG_CWARPS; ++w) pw[w] = rp[w * (NT * 16 * MT)];
-#pragma unroll
-                                for (int st = 1; st < MG_CWARPS; st <<= 1)
-#pragma unroll
-                                    for (int w = 0; w < MG_CWARPS; w += 2 * st) pw[w] += pw[w + st];
-                                v = pw[0];
-                                if (S > 1) {
-                                    float *at = acc_tile + (size_t)(it + r_slot) * 16 * MT + (rt % (16 * MT));
-                                    if (s > 0) v += *at;
-                                    if (s + 1 < S) *at = v;
-                                }
-                            }
-                            if (s + 1 == S) {
-                                const bool live = r_valid && r_tok < B;
-                                if (has_norm && live) v *= rinv[r_tok];
-                                float fval = 0.0f;  // what the next matvec consumes (0 for padding rows)
-                                if (epi == EPI_SILU_MUL) {
-                                    const float o = __shfl_xor_sync(0xffffffffu, v, 1);
-                                    if (live && !(r_r & 1) && r_row + 1 < N) {
-                                        fval = (v / (1.0f + expf(-v))) * o;
-                                        if (yout) yout[(size_t)r_tok * ldy + (r_row >> 1)] = fval;
-                                    }
-                                } else {
-                                    float out = 0.0f;
-                                    if (live && r_row < N) {
-                                        out = v + (bias ? bias[r_row] : 0.0f);
-                                        if (epi == EPI_RESIDUAL) out += res_pre;
-                                        if (epi == EPI_GELU) out = 0.5f * out * (1.0f + erff(out * 0.70710678118654752440f));
-                                        if (yout) yout[(size_t)r_tok * ldy + r_row] = out;
-                                        if (track) amax_combine(best_v, best_i, out, r_row);
-                                    }
-                                    fval = out;
-                                    if (ssq_out) {
-                                        float sq = out * out;
-                                        sq += __shfl_xor_sync(0xffffffffu, sq, 8);
-                                        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-                                        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-                                        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                                        if (live && r_r == 0) ssq_out[(size_t)r_tile * B + r_tok] = sq;
-                                    }
-                                }
-                                if (fout_bf) {
-                                    // ---- this group's outputs become the next matvec's activation fragments:
-                                    // a unit of UT consecutive tiles = one 32-value block per token
-                                    const int li = it + r_slot;                       // index in the CTA's tile list
-                                    const int be = UT <= NT ? r_slot / UT : 0;        // block within this group
-                                    const int ti = li % UT;                           // tile within its unit
-                                    rbar<RW>();  // the previous group's builders are done with vals
-                                    if (live) {
-                                        if (epi == EPI_SILU_MUL) {
-                                            if (!(r_r & 1)) vals[(be * 32 + ti * 8 + (r_r >> 1)) * MT + r_tok] = fval;
-                                        } else {
-                                            vals[(be * 32 + ti * 16 + r_r) * MT + r_tok] = fval;
-                                        }
-                                    }
-                                    rbar<RW>();
-                                    if (rt < ((2 * 4 * MT + 31) / 32) * 32) {  // warp-uniform: the warps holding builder lanes (rt >= 0 here)
-                                        float4 l = make_float4(0.f, 0.f, 0.f, 0.f), h = l;
-                                        if (bact) {
-                                            const float *vb = vals + (size_t)(bi * 32) * MT + bm_;
-                                            l = make_float4(vb[(4 * bt + 0) * MT], vb[(4 * bt + 1) * MT], vb[(4 * bt + 2) * MT], vb[(4 * bt + 3) * MT]);
-                                            h = make_float4(vb[(16 + 4 * bt + 0) * MT], vb[(16 + 4 * bt + 1) * MT], vb[(16 + 4 * bt + 2) * MT],
-                                                            vb[(16 + 4 * bt + 3) * MT]);
-                                            l = mul4(l, fg_lo);
-                                            h = mul4(h, fg_hi);
-                                        }
-                                        frag_build<MT>(l, h, bact, bt, bm_, fout_bf + (size_t)f_blk * (16 * MT), fout_off + (size_t)f_blk * MT);
-                                    }
-                                }
-                            }
-                        }
+                        ++group_ctr;
                         if (tw) tw[6] = (unsigned long long)clock64();
                         par ^= 1;
                     }
-                }
-            }
-            if (fout_bf) asm volatile("fence.proxy.async;\n" ::: "memory");  // fragments are read by bulk copies next phase
-            if (track) {
-                // this CTA's best candidate per stream (lowest index wins ties: order independent).  Every warp may have been
-                // a reducer (rotating sets); a thread's (tile slot, token) is the same in every group it reduced:
-                // first the 16 rows of a (slot, token) group, then the sets and slots through shared memory
-                const int rta = tid % (RW * 32), rset = warp / RW;
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
-                    const int ox = __shfl_xor_sync(0xffffffffu, best_i, o);
-                    amax_combine(best_v, best_i, ov, ox);
-                }
-                // `vals` is idle in this op (only fragment-producing ops use it) -- not `red`, which slower epilogue
-                // warps may still be reading: [NSETS][NT][MT] values, then as many indices
-                float *cv = vals;
-                int *ci = reinterpret_cast<int *>(vals + NSETS * NT * MT);
-                if ((rta & 15) == 0 && rta < NT * 16 * MT) {
-                    cv[rset * (NT * MT) + (rta >> 4)] = best_v;
-                    ci[rset * (NT * MT) + (rta >> 4)] = best_i;
-                }
-                best_v = -INFINITY;
-                best_i = 0x7fffffff;
-                cbar();
-                if (tid < B) {
-                    float bv = -INFINITY;
-                    int bx = 0x7fffffff;
-#pragma unroll
-                    for (int u = 0; u < NSETS * NT; ++u) amax_combine(bv, bx, cv[u * MT + tid], ci[u * MT + tid]);
-                    p.am_vals[(size_t)cta * 8 + tid] = bv;
-                    p.am_idx[(size_t)cta * 8 + tid] = bx;
                 }
             }
         } else if (kind == MG_ATTN) {
@@ -1107,7 +1226,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         if (tr_all) ta[1] = ta[2] = (unsigned long long)clock64();
         // ---- grid barrier between phases
         if (oi + 1 < p.n_ops) {
-            cbar();
+            abar();   // consumers + epilogue warps: every store of this phase precedes thread 0's arrival
             if (tid == 0) {
                 // release: ordered after every consumer thread's stores by the barrier above (cumulativity);
                 // acquire: the spin load; the barrier below extends it to the CTA
@@ -1121,7 +1240,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 }
                 asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
             }
-            cbar();
+            abar();
             if (tracing) p.trace[oi * 6 + 3] = (unsigned long long)clock64();
             if (tr_all) ta[2] = (unsigned long long)clock64();
         }
