@@ -797,9 +797,10 @@ int32_t vox_session_debug_read(vox_session *sh, const char *what, float *out, si
         if (n_floats) *n_floats = 0;
         return VOX_OK;
     } else if (w == "mega_off" || w == "mega_on" || w == "mega_auto") {
-        // mega_on: persistent decode kernel for every batch size; mega_auto: default policy (B >= 2)
+        // mega_on / mega_auto: persistent decode kernel for every batch size (the default policy since round 2: it is no
+        // slower than the per-op launches even for a single stream); mega_off: per-op launches
         s->use_mega = (w != "mega_off");
-        s->mega_min_B = (w == "mega_on") ? 1 : 2;
+        s->mega_min_B = 1;
         s->mega_B = 0;
         if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
         if (n_floats) *n_floats = 0;

@@ -6,22 +6,25 @@
 // last 1-5 us (profiles/README.md, r01b): launch gaps, per-kernel activation staging and CTA-wide
 // barriers dominate.  Here one CTA per SM lives for the whole step:
 //
-//   * 16 consumer warps + 1 producer warp.  The producer thread walks the step's entire weight
-//     schedule (every matvec of every layer, in order) and streams this CTA's share through a ring
-//     of TMA bulk-copy stages (16 block pairs = 9 KB each, full/empty mbarriers).  It never waits
-//     for activations, so the HBM stream runs ahead across op boundaries: while the consumers sit
-//     in a grid barrier or stage the next op's activations, the ring (100-180 KB) keeps filling.
-//   * a phase (op) = embed | matvec | attention | argmax; consecutive phases are separated by a
-//     grid barrier (one atomic arrival per CTA, acquire spin by one thread).
-//   * matvec arithmetic is matvec_tc.cu's: Q4 nibbles enter mma.sync.m16n8k16 as f16 subnormals,
-//     activations as per-block power-of-two scaled f16 hi+mid pieces, the block scale d applied to
-//     the f32 block sum (shader.wgsl:96-127 re-associated).  A CTA owns whole 16-row tiles
-//     (tile = cta, cta+grid, ...): the 16 warps take one block pair each of every stage, partial sums
-//     meet in shared memory once per tile (ONE named barrier per tile, double-buffered), 16*M
-//     threads add them in fixed warp order and run the epilogue (bias / residual + sums of squares
-//     for the next fused RMSNorm / SiLU*up / running argmax) => no atomics, no split-K scratch,
-//     bitwise deterministic.  When the activation fragments of all of K do not fit shared memory
-//     (M > 2 and K > 3072) the CTA walks K in private slices and keeps tile sums in shared memory.
+//   * 20 warps in three roles: 16 consumer warps (the weight stream's arithmetic, attention, embedding), and one
+//     warpgroup of helpers: the producer warp and 3 epilogue warps.  The launch gives every thread 96 registers;
+//     setmaxnreg moves the helpers' surplus to the consumers (64 / 104).  Spills are poison here: 227 KB of the SM's 256 KB
+//     are shared memory, there is no L1 left to catch local-memory traffic, every reload is an L2 round trip.
+//   * The producer thread walks the step's entire weight schedule (every matvec of every layer, in order) and streams
+//     this CTA's share through a ring of TMA bulk-copy stages (16 block pairs = 9 KB per tile, full/empty mbarriers).  It
+//     never waits for activations, so the HBM stream runs ahead across op boundaries: while the consumers sit in a grid
+//     barrier or stage the next op's activations, the ring (90-180 KB) keeps filling.
+//   * a phase (op) = embed | matvec | attention | argmax; consecutive phases are separated by a grid barrier (one atomic
+//     arrival per CTA, acquire spin by one thread).
+//   * matvec arithmetic is matvec_tc.cu's: Q4 nibbles enter mma.sync.m16n8k16 as f16 subnormals, activations as per-block
+//     power-of-two scaled f16 hi+mid pieces, the block scale d applied to the f32 block sum (shader.wgsl:96-127
+//     re-associated).  A CTA owns whole 16-row tiles (tile = cta, cta+grid, ...): the 16 consumer warps take one block pair
+//     each of every stage; their partial sums of a tile group go to shared memory (double-buffered) and are handed to the
+//     epilogue warps through named arrive/wait barriers -- the consumers go straight on to the next group's stream.  The
+//     epilogue warps add the 16 partials in fixed tree order and run the epilogue (bias / residual + sums of squares for the
+//     next fused RMSNorm / SiLU*up / running argmax / activation fragments of the next matvec) => no atomics, no split-K
+//     scratch, bitwise deterministic.  When the activation fragments of all of K do not fit shared memory (M > 2 and
+//     K > 3072) the CTA walks K in private slices and keeps tile sums in shared memory.
 //   * attention: RoPE + KV append + GQA as in decode_attn.cu, one CTA per (stream, kv head).
 //
 // All activations written by other CTAs are read with ld.global.cg (L1 is not coherent).
@@ -47,9 +50,9 @@ inline void cuda_check_mg(cudaError_t e, const char *what) {
 
 constexpr int MG_CWARPS = 16;                    // consumer warps
 constexpr int MG_CTHREADS = MG_CWARPS * 32;
-// + the producer's warpgroup: warp 16 is the producer, warps 17-19 exist only so that the warpgroup can hand most of its
-// registers to the consumers (setmaxnreg works on whole warpgroups of 4 warps).  The register file is allocated in units of
-// 4 warps anyway: 17 warps cost as many registers as 20.
+// + the helpers' warpgroup: warp 16 is the producer, warps 17-19 run the matvec epilogues; the warpgroup hands a third of
+// its registers to the consumers (setmaxnreg works on whole warpgroups of 4 warps).  The register file is allocated in
+// units of 4 warps anyway: 17 warps cost as many registers as 20.
 constexpr int MG_THREADS = MG_CTHREADS + 128;
 constexpr int MG_REGS_CONSUMER = 104;            // 16 x 32 x (104 - 96) = 4096 registers moved ...
 constexpr int MG_REGS_PRODUCER = 64;             // ... from the producer / epilogue warpgroup: 4 x 32 x (96 - 64) = 4096
@@ -155,12 +158,6 @@ __device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gm
             smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
         : "memory");
-}
-// barrier among the first NW warps (the epilogue warps of a matvec phase)
-template <int NW>
-__device__ __forceinline__ void rbar() {
-    if (NW == 1) __syncwarp();
-    else asm volatile("bar.sync 2, %0;\n" ::"n"(NW * 32) : "memory");
 }
 // barrier among the 512 consumer threads (the producer warp never joins)
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
@@ -371,7 +368,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     constexpr int HD = DPL * 32;
     static_assert(G * HD <= MG_CTHREADS, "one attention output per consumer thread");
     constexpr int NT = mg_nt(MT);
-    constexpr int RW = (NT * 16 * MT + 31) / 32;  // warps that add the per-warp partial sums and run the epilogue
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + MG_MAX_STAGES;

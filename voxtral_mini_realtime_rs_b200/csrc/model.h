@@ -136,7 +136,7 @@ struct Session {
     // persistent decode-step kernel (decode_mega.cu): op table per batch size, grid barrier words,
     // per-CTA argmax candidates.  VOX_MEGA=0 (or debug "mega_off") selects the per-op launches.
     bool use_mega = true;
-    int mega_min_B = 2;  // a single stream is (slightly) faster through the per-op launches (profiles/README.md)
+    int mega_min_B = 1;  // (round 1: a single stream was slightly faster through the per-op launches; no longer -- profiles/README.md)
     int mega_B = 0, mega_grid = 0, mega_n_ops = 0, mega_ops_cap = 0;
     MegaPlan mega_plan;
     std::vector<MegaOp> mega_ops_host;
