@@ -78,9 +78,9 @@ __host__ __device__ constexpr int mg_vals(int MT) { return (MT <= 2 ? 2 : 1) * 3
 static_assert(mg_vals(1) >= 2 * mg_nt(1) * 1 && mg_vals(2) >= 2 * mg_nt(2) * 2 && mg_vals(4) >= 2 * mg_nt(4) * 4 &&
                   mg_vals(8) >= 2 * mg_nt(8) * 8,
               "vals also holds the lm_head phase's per-slot argmax candidates");
-// barriers + rinv + red[2][16 warps][NT*16*MT] + acc_tile[MG_ACC_TILES][16*MT] + vals
+// barriers + rinv + rpart[4][8] + stgc[4] + red[2][16 warps][NT*16*MT] + acc_tile[MG_ACC_TILES][16*MT] + vals
 __host__ __device__ constexpr int mg_misc_bytes(int MT) {
-    return ((432 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT + 4 * mg_vals(MT) + 256) + 127) & ~127;  // + s_op
+    return ((592 + 2048 * mg_nt(MT) * MT + 64 * MG_ACC_TILES * MT + 4 * mg_vals(MT) + 256) + 127) & ~127;  // + s_op
 }
 __host__ __device__ constexpr int mg_pair_bytes(int MT) { return 272 * MT; }  // fragments + offsets of one block pair
 
@@ -372,7 +372,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + MG_MAX_STAGES;
     float *rinv = reinterpret_cast<float *>(empty + MG_MAX_STAGES + 2);  // [8]
-    float *red = rinv + 8;                                            // [2][MG_CWARPS][NT*16*MT]
+    float *rpart = rinv + 8;                                          // [4 warps][8 tokens] partial sums of squares
+    uint64_t *stgc = reinterpret_cast<uint64_t *>(rpart + 32);        // [4] activation fragments of K chunk c landed in scratch
+    float *red = reinterpret_cast<float *>(stgc + 4);                 // [2][MG_CWARPS][NT*16*MT]
     float *acc_tile = red + 2 * MG_CWARPS * NT * 16 * MT;             // [MG_ACC_TILES][16*MT]
     float *vals = acc_tile + MG_ACC_TILES * 16 * MT;                  // [1 or 2 blocks][32][MT]
     MegaOp *s_op = reinterpret_cast<MegaOp *>(vals + mg_vals(MT));  // the current op's descriptor for the epilogue warps
@@ -392,6 +394,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             mbar_init(&empty[i], MG_CWARPS);
         }
         mbar_init(stg, 1);
+        for (int c = 0; c < 4; ++c) mbar_init(&stgc[c], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -634,7 +637,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                                         float sq = (out.x * out.x + out.y * out.y) + (out.z * out.z + out.w * out.w);
                                         sq += __shfl_xor_sync(0xffffffffu, sq, 2);
                                         sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                                        if (live && q_r0 == 0) ssq_out[(size_t)r_tile * B + q_tok] = sq;
+                                        if (live && q_r0 == 0) ssq_out[(size_t)r_tile * 8 + q_tok] = sq;   // [part][8 tokens]
                                     }
                                 }
                                 if (fout_bf) {
@@ -769,46 +772,52 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 for (int s = 0; s < S; ++s) {
                     const int pb = s * Ps;
                     const int np = min(Ps, n_pairs - pb);
-                    cbar();  // every warp is done with the previous contents of scratch
+                    // The fragments land in up to 4 K chunks (whole ring stages of 16 pairs), each with its own barrier: the
+                    // first tile group starts on chunk 0 while the rest of the copy is still in flight (the copy is L2-bandwidth
+                    // bound: all 148 CTAs fetch the same 70-104 KB).
+                    const int CP = 16 * ((((np + 15) >> 4) + 3) >> 2);  // pairs per chunk
+                    cbar();  // every warp is done with the previous contents of scratch (and has seen all its chunks)
                     if (tid == 0) {
                         // the input's fragments were written (generic proxy, other SMs) before the grid barrier
                         asm volatile("fence.proxy.async;\n" ::: "memory");
-                        const uint32_t ob = (uint32_t)(2 * np * MT) * 8u, bb = (uint32_t)(2 * np * MT) * 128u;
-                        mbar_expect_tx(stg, ob + bb);
+                        const uint32_t ob = (uint32_t)(2 * np * MT) * 8u;
                         const unsigned char *src = reinterpret_cast<const unsigned char *>(op.fin_bf + (size_t)(2 * pb) * (16 * MT));
                         unsigned char *dstb = reinterpret_cast<unsigned char *>(bf);
-                        bulk_g2s(off2, op.fin_off + (size_t)(2 * pb) * MT, ob, stg);
-                        // every CTA copies the same fragments: start each CTA at a different eighth so that the 148
-                        // copies do not sweep the same L2 slices in lock step
-                        if ((p.flags & 8) || bb < 8u * 1024u) {
-                            bulk_g2s(dstb, src, bb, stg);
-                        } else {
-                            const uint32_t chunk = ((bb / 8u) + 15u) & ~15u;
-                            for (int q = 0; q < 8; ++q) {
-                                const uint32_t o = (uint32_t)((q + cta) & 7) * chunk;
-                                if (o < bb) bulk_g2s(dstb + o, src + o, min(chunk, bb - o), stg);
-                            }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int p0 = min(np, c * CP), p1 = min(np, (c + 1) * CP);
+                            const uint32_t o = (uint32_t)p0 * (256u * MT), cb = (uint32_t)(p1 - p0) * (256u * MT);
+                            mbar_expect_tx(&stgc[c], cb + (c == 0 ? ob : 0u));   // an empty chunk completes at once
+                            if (c == 0) bulk_g2s(off2, op.fin_off + (size_t)(2 * pb) * MT, ob, &stgc[0]);
+                            if (cb) bulk_g2s(dstb + o, src + o, cb, &stgc[c]);
                         }
                     }
-                    // row statistics of the fused RMSNorm (first used by the epilogue)
-                    if (s == 0 && has_norm && warp < B) {
-                        float ss = 0.0f;
-                        float pr[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const int i = lane + 32 * q;
-                            pr[q] = i < op.ssq_in_parts ? __ldcg(op.ssq_in + (size_t)i * B + warp) : 0.0f;
-                        }
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) ss += pr[q];
-                        for (int i = lane + 256; i < op.ssq_in_parts; i += 32) ss += __ldcg(op.ssq_in + (size_t)i * B + warp);
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                        if (lane == 0) rinv[warp] = 1.0f / sqrtf(ss / (float)K + p.eps);
-                    }
-                    mbar_wait(stg, stg_phase, wd_flag, 0x500u + (unsigned)oi);
+                    const uint32_t stg_par = stg_phase;
                     stg_phase ^= 1u;
-                    cbar();  // rinv visible to the epilogue threads
+                    // row statistics of the fused RMSNorm (first used by the epilogue).  The partial sums live as
+                    // [part][8 tokens]: warps 1..4 read them with coalesced loads (lane % 8 = token).  (One warp per token reading
+                    // its column cost 2048 sector requests per CTA for the same 6 KB, by all 148 CTAs at once: the normed phases'
+                    // staging was ~1 us longer than the others'.)
+                    if (s == 0 && has_norm && warp >= 1 && warp <= 4) {
+                        const int total = op.ssq_in_parts * 8;
+                        float pr[12];
+#pragma unroll
+                        for (int q = 0; q < 12; ++q) {
+                            const int f = (warp - 1) * 32 + lane + 128 * q;
+                            pr[q] = f < total ? __ldcg(op.ssq_in + f) : 0.0f;
+                        }
+                        float ss = 0.0f;
+#pragma unroll
+                        for (int q = 0; q < 12; ++q) ss += pr[q];
+                        for (int f = (warp - 1) * 32 + lane + 128 * 12; f < total; f += 128) ss += __ldcg(op.ssq_in + f);
+                        ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+                        ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+                        if (lane < 8) rpart[(warp - 1) * 8 + lane] = ss;
+                    }
+                    cbar();  // the warps' partial sums are visible
+                    // 1/rms per token: read by the epilogue warps behind the first tile group's hand-off barrier
+                    if (s == 0 && has_norm && tid < B)
+                        rinv[tid] = 1.0f / sqrtf((((rpart[tid] + rpart[8 + tid]) + (rpart[16 + tid] + rpart[24 + tid]))) / (float)K + p.eps);
                     if (tracing && s == 0) p.trace[oi * 6 + 1] = (unsigned long long)clock64();
                     // the CTA's tiles NT at a time: every warp carries NT independent accumulation chains that
                     // share one read of the activation fragments
@@ -834,7 +843,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         {
                             const uint32_t slot_q = (uint32_t)warp * 512u + (uint32_t)lane * 16u;
                             const uint32_t slot_d = (uint32_t)MG_SLOT_Q + (uint32_t)warp * 64u + (uint32_t)g * 8u;
+                            int next_chunk_c0 = it == 0 ? 0 : 0x7fffffff, chunk = 0;   // first pass over the slice: wait per chunk
                             for (int c0 = 0; c0 < np; c0 += MG_CHUNK) {
+                                if (c0 == next_chunk_c0) {   // the fragments of this K chunk must have landed
+                                    mbar_wait(&stgc[chunk], stg_par, wd_flag, 0x500u + (unsigned)oi);
+                                    ++chunk;
+                                    next_chunk_c0 += CP;
+                                }
                                 mbar_wait(&full[stage], phase, wd_flag, 0x200u + (unsigned)oi);
                                 if (tracing && s == 0 && it == 0 && c0 == 0) p.trace[oi * 6 + 4] = (unsigned long long)clock64();
                                 if (tr_all && s == 0 && it == 0 && c0 == 0) ta[3] = (unsigned long long)clock64();
@@ -1170,8 +1185,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         sh += __shfl_xor_sync(0xffffffffu, sh, o);
                     }
                     if (act && j == 0) {
-                        p.ssq_x[(size_t)(2 * blk) * B + b] = sl;
-                        p.ssq_x[(size_t)(2 * blk + 1) * B + b] = sh;
+                        p.ssq_x[(size_t)(2 * blk) * 8 + b] = sl;
+                        p.ssq_x[(size_t)(2 * blk + 1) * 8 + b] = sh;
                     }
                 }
                 cbar();
