@@ -131,12 +131,14 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_s32(int *p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+// A float published together with its validity tag in ONE 8-byte word (single-copy atomic): the reader polls the word
+// itself -- no flag, no fence, no second round trip.
+__device__ __forceinline__ void st_tagged(float2 *p, const float v, const int tag) {
+    asm volatile("st.relaxed.gpu.global.v2.f32 [%0], {%1, %2};\n" ::"l"(p), "f"(v), "f"(__int_as_float(tag)) : "memory");
 }
-__device__ __forceinline__ int ld_acquire_s32(const int *p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ float2 ld_tagged(const float2 *p) {
+    float2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void red_release_add(unsigned *p, unsigned v) {
@@ -1060,7 +1062,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                 // ---- combine the warps; with several key chunks per (stream, kv head) the last chunk's CTA also
                 // combines the chunks (pairwise release/acquire flags: no grid-wide phase for the merge)
                 const int u0 = bk * NC;
-                const int target = epoch * 64 + op.layer + 1;  // unique per (decode step, layer), monotonic
+                const int target = epoch * 64 + op.layer + 1;  // unique per (decode step, layer), never 0
+                float2 *const acc2 = reinterpret_cast<float2 *>(p.att_acc);   // [unit][G][hd] {value, tag}
+                float2 *const ml2 = reinterpret_cast<float2 *>(p.att_ml);     // [unit][G][2]  {value, tag}
                 float o_final = 0.0f;                           // thread i < G*HD: output (head i / HD, dim i % HD)
                 for (int i = tid; i < G * HD; i += MG_CTHREADS) {
                     const int h = i / HD, d = i - h * HD;
@@ -1075,60 +1079,43 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         num = fmaf(red_acc[((size_t)w * G + h) * HD + d], f, num);
                         den = fmaf(red_l[w * G + h], f, den);
                     }
-                    if (NC > 1) {
-                        p.att_acc[((size_t)unit * G + h) * HD + d] = num;
+                    if (NC == 1) {
+                        o_final = num / den;
+                    } else if (ch != NC - 1) {
+                        // publish this chunk's state; every word carries the (step, layer) tag, so the merging CTA polls the
+                        // words themselves: no CTA barrier, fence and flag on this side, no flag wait + reload on the other
+                        st_tagged(acc2 + ((size_t)unit * G + h) * HD + d, num, target);
                         if (d == 0) {
-                            p.att_ml[((size_t)unit * G + h) * 2 + 0] = mx;
-                            p.att_ml[((size_t)unit * G + h) * 2 + 1] = den;
+                            st_tagged(ml2 + ((size_t)unit * G + h) * 2 + 0, mx, target);
+                            st_tagged(ml2 + ((size_t)unit * G + h) * 2 + 1, den, target);
                         }
                     } else {
-                        o_final = num / den;
-                    }
-                }
-                if (NC > 1) {
-                    cbar();  // the CTA's chunk state is written
-                    if (tid == 0) {
-                        __threadfence();
-                        st_release_s32(p.att_flags + unit, target);
-                    }
-                    if (ch != NC - 1) continue;  // only the last chunk's CTA goes on to merge
-                    if (tid < NC - 1) {
+                        // the last chunk's CTA combines the chunks: its own state from registers, the others' as they arrive
+                        // (online rescaling, ascending chunk order: a few registers whatever the chunk count)
+                        float m_all = mx, nsum = num, dsum = den;
                         const long long t0 = clock64();
-                        unsigned n = 0;
-                        while (ld_acquire_s32(p.att_flags + u0 + tid) < target) {
-                            if ((++n & 0x3FFu) == 0 && clock64() - t0 > MG_SPIN_CYCLES) mg_die(wd_flag, 0x600u + (unsigned)oi);
-                        }
-                    }
-                    cbar();
-                    for (int i = tid; i < G * HD; i += MG_CTHREADS) {
-                        const int h = i / HD, d = i - h * HD;
-                        float mc[16], lc[16], ac[16];
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) {  // all loads first (in-order issue: a use would serialise them)
-                            mc[c] = -INFINITY;
-                            lc[c] = 0.0f;
-                            ac[c] = 0.0f;
-                            if (c < NC) {
-                                mc[c] = __ldcg(p.att_ml + ((size_t)(u0 + c) * G + h) * 2 + 0);
-                                lc[c] = __ldcg(p.att_ml + ((size_t)(u0 + c) * G + h) * 2 + 1);
-                                ac[c] = __ldcg(p.att_acc + ((size_t)(u0 + c) * G + h) * HD + d);
+                        for (int c = 0; c < NC - 1; ++c) {
+                            const float2 *pa = acc2 + ((size_t)(u0 + c) * G + h) * HD + d;
+                            const float2 *pm = ml2 + ((size_t)(u0 + c) * G + h) * 2;
+                            float2 va = ld_tagged(pa), vm = ld_tagged(pm), vl = ld_tagged(pm + 1);
+                            unsigned n = 0;
+                            while (__float_as_int(va.y) != target || __float_as_int(vm.y) != target || __float_as_int(vl.y) != target) {
+                                if ((++n & 0x3FFu) == 0 && clock64() - t0 > MG_SPIN_CYCLES) mg_die(wd_flag, 0x600u + (unsigned)oi);
+                                if (__float_as_int(va.y) != target) va = ld_tagged(pa);
+                                if (__float_as_int(vm.y) != target) vm = ld_tagged(pm);
+                                if (__float_as_int(vl.y) != target) vl = ld_tagged(pm + 1);
                             }
+                            const float m_new = fmaxf(m_all, vm.x);
+                            const float fo = (m_all == -INFINITY) ? 0.0f : fast_exp(m_all - m_new);
+                            const float fc = (vm.x == -INFINITY) ? 0.0f : fast_exp(vm.x - m_new);
+                            nsum = fmaf(va.x, fc, nsum * fo);
+                            dsum = fmaf(vl.x, fc, dsum * fo);
+                            m_all = m_new;
                         }
-                        float mx = -INFINITY;
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) mx = fmaxf(mx, mc[c]);
-                        float num = 0.0f, den = 0.0f;
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            if (c < NC) {
-                                const float f = (mc[c] == -INFINITY) ? 0.0f : fast_exp(mc[c] - mx);
-                                num = fmaf(ac[c], f, num);
-                                den = fmaf(lc[c], f, den);
-                            }
-                        }
-                        o_final = num / den;
+                        o_final = nsum / dsum;
                     }
                 }
+                if (NC > 1 && ch != NC - 1) continue;  // only the last chunk's CTA produces the output
                 // ---- attention output + its fragments for wo: a warp holds 32 consecutive dims of one head = one block
                 if (tid < ((G * HD + 31) / 32) * 32) {
                     const bool oact = tid < G * HD;

@@ -507,11 +507,14 @@ Session *Session::create(Model *m, int max_batch, int max_mel_frames) {
             s->mega_am_vals = s->arena.alloc_n<float>((size_t)s->mega_grid * 8);
             s->mega_am_idx = s->arena.alloc_n<int>((size_t)s->mega_grid * 8);
             s->mega_att_units = std::max(s->mega_grid, 8 * c.dec_kv_heads) + 8 * c.dec_kv_heads;
-            s->mega_att_acc = s->arena.alloc_n<float>((size_t)s->mega_att_units * (c.dec_heads / c.dec_kv_heads) * c.dec_head_dim);
-            s->mega_att_ml = s->arena.alloc_n<float>((size_t)s->mega_att_units * (c.dec_heads / c.dec_kv_heads) * 2);
+            s->mega_att_acc = s->arena.alloc_n<float>((size_t)2 * s->mega_att_units * (c.dec_heads / c.dec_kv_heads) * c.dec_head_dim);  // {value, tag}
+            s->mega_att_ml = s->arena.alloc_n<float>((size_t)2 * s->mega_att_units * (c.dec_heads / c.dec_kv_heads) * 2);  // {value, tag}
             s->mega_att_flags = s->arena.alloc_n<int>(s->mega_att_units);
             s->mega_epoch = s->arena.alloc_n<int>(1);
             CUDA_OK(cudaMemset(s->mega_att_flags, 0, sizeof(int) * s->mega_att_units));
+            // chunk states carry their own validity tag (decode step, layer): never 0
+            CUDA_OK(cudaMemset(s->mega_att_acc, 0, sizeof(float) * 2 * s->mega_att_units * (c.dec_heads / c.dec_kv_heads) * c.dec_head_dim));
+            CUDA_OK(cudaMemset(s->mega_att_ml, 0, sizeof(float) * 2 * s->mega_att_units * (c.dec_heads / c.dec_kv_heads) * 2));
             CUDA_OK(cudaMemset(s->mega_epoch, 0, sizeof(int)));
             {
                 auto blocks = [](int K) { return (size_t)((K / 32 + 1) / 2) * 2; };
