@@ -18,6 +18,8 @@ constexpr int MT = 8;
 
 // MODE bits: 1 = no MMA (cc = float(a-bits) instead), 2 = weights not re-read from shared memory (first iteration's
 // registers reused), 4 = fragments not re-read, 8 = no scale FMAs, 16 = chains interleaved in source order
+// MODE bit 32: the ring holds random bytes, i.e. the A operands are f16 SUBNORMALS n * 2^-24 / n * 2^-20 as in the kernel
+// (the default fill masks to 0x3C00 patterns, which the nibble masks turn into zeros)
 template <int MODE>
 __global__ void __launch_bounds__(544, 1) body_kernel(unsigned long long *out, int iters, float *sink, int maxreg_dummy) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -26,7 +28,7 @@ __global__ void __launch_bounds__(544, 1) body_kernel(unsigned long long *out, i
     float2 *off2 = reinterpret_cast<float2 *>(bf + 16 * 2 * 16 * MT);  // [16 pairs][2][MT]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     for (int i = tid; i < (4 * 2 * SLOT + 16 * 2 * 16 * MT * 8 + 16 * 2 * MT * 8) / 4; i += blockDim.x)
-        reinterpret_cast<uint32_t *>(smem)[i] = (uint32_t)i * 2654435761u & 0x3C003C00u;  // finite halves
+        reinterpret_cast<uint32_t *>(smem)[i] = ((MODE & 32) && i < 4 * 2 * SLOT / 4) ? ((uint32_t)i * 2654435761u) ^ ((uint32_t)i >> 3) : ((uint32_t)i * 2654435761u & 0x3C003C00u);  // finite halves
     __syncthreads();
     float acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     const uint32_t slot_q = (uint32_t)warp * 512u + (uint32_t)lane * 16u;
@@ -142,6 +144,8 @@ void run(const char *name) {
 
 int main() {
     run<0>("full body (16 HMMA, unpack, scale FMAs, LDS)");
+    run<32>("full body, subnormal A operands (random nibbles)");
+    run<32 + 14>("MMA + unpack only, subnormal A operands");
     run<16>("full body, chains interleaved in source");
     run<1>("no MMA");
     run<2>("weights kept in registers (no LDS of qs/d)");

@@ -895,7 +895,10 @@ void Session::decode_step_mega(int b0, int B, bool add_audio) {
         p.cos_t = m->dec_cos;
         p.sin_t = m->dec_sin;
         p.attn_out = attn_dec;
-        p.attn_chunks = std::max(1, std::min(16, std::min(mega_grid, mega_att_units - 8 * c.dec_kv_heads) / (B * c.dec_kv_heads)));
+        // key chunks per (stream, kv head): spread the KV walk over idle SMs, but no more than 4 -- the merging CTA waits
+        // for the other chunks' states one after the other (an L2 round trip each), and a CTA walks 64 keys per round
+        // trip anyway: 16 chunks made a single stream's attention phase slower than 4 (12.1 vs ~9 us at 16 s contexts)
+        p.attn_chunks = std::max(1, std::min(4, std::min(mega_grid, mega_att_units - 8 * c.dec_kv_heads) / (B * c.dec_kv_heads)));
         {
             static const int env_nc = getenv("VOX_MEGA_NC") ? atoi(getenv("VOX_MEGA_NC")) : 0;
             if (env_nc > 0 && env_nc <= p.attn_chunks) p.attn_chunks = env_nc;
