@@ -25,7 +25,8 @@
 //     next fused RMSNorm / SiLU*up / running argmax / activation fragments of the next matvec) => no atomics, no split-K
 //     scratch, bitwise deterministic.  When the activation fragments of all of K do not fit shared memory (M > 2 and
 //     K > 3072) the CTA walks K in private slices and keeps tile sums in shared memory.
-//   * attention: RoPE + KV append + GQA as in decode_attn.cu, one CTA per (stream, kv head).
+//   * attention: RoPE + KV append + GQA as in decode_attn.cu, one CTA per (stream, kv head, key chunk); the chunks' softmax
+//     states travel as 8-byte {value, (step, layer) tag} words that the merging CTA polls directly.
 //
 // All activations written by other CTAs are read with ld.global.cg (L1 is not coherent).
 // Every spin loop has a watchdog that traps instead of hanging the GPU.
@@ -917,7 +918,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             }
         } else if (kind == MG_ATTN) {
             // unit = (stream, kv head, key chunk): the 4 query heads of a GQA group share one pass over their
-            // chunk of K and V; the chunks' softmax states are combined in the MG_ATTN_MERGE phase.  (One CTA
+            // chunk of K and V; the chunks' softmax states are combined by the last chunk's CTA (tagged words, below).  (One CTA
             // per (stream, kv head) walked all keys in ~17 us -- issue-bound -- while 140 SMs waited.)
             float *qs = reinterpret_cast<float *>(scratch);       // [G][HD]
             float *kvs = qs + G * HD;                              // [2][HD]

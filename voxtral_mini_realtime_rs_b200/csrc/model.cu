@@ -967,10 +967,15 @@ void Session::reset() {
     CUDA_OK(cudaMemsetAsync(d_pos, 0, sizeof(int) * max_batch, st));
     CUDA_OK(cudaMemsetAsync(d_outpos, 0, sizeof(int) * max_batch, st));
     cache_len = 0;
-    // the persistent kernel's attention-chunk flags carry epoch * 64 + layer + 1 (int): re-base the device
-    // epoch long before that can overflow (2^24 steps ~ 10 hours of continuous decoding)
+    // the persistent kernel's attention-chunk states carry the tag epoch * 64 + layer + 1 (int): re-base the device
+    // epoch long before that can overflow (2^24 steps ~ 10 hours of continuous decoding) -- and wipe the tagged words, so
+    // that no stale state can match a tag of the new numbering
     if (mega_steps_host > (1u << 24)) {
+        const vox_model_info &ci = m->info;
+        const size_t gq = (size_t)(ci.dec_heads / ci.dec_kv_heads);
         CUDA_OK(cudaMemsetAsync(mega_att_flags, 0, sizeof(int) * mega_att_units, st));
+        CUDA_OK(cudaMemsetAsync(mega_att_acc, 0, sizeof(float) * 2 * mega_att_units * gq * ci.dec_head_dim, st));
+        CUDA_OK(cudaMemsetAsync(mega_att_ml, 0, sizeof(float) * 2 * mega_att_units * gq * 2, st));
         CUDA_OK(cudaMemsetAsync(mega_epoch, 0, sizeof(int), st));
         mega_steps_host = 0;
     }
