@@ -496,6 +496,32 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
                         ebar();
                     }
                     const volatile MegaOp *const vop = s_op;
+                    // (run by the last epilogue thread, which has nothing to do until the first tile group arrives: on the
+                    // consumers' thread 0 the dependent loads of positions and page table delayed the fragment copies of the
+                    // qkv phase by ~1.3 us)
+                    if (e == MG_ETHREADS - 1 && oi + 1 < p.n_ops && !(p.flags & 2)) {
+                        // the next phase is this layer's attention: pull this CTA's chunk of the KV cache into L2 now, so the
+                        // walk does not wait on DRAM behind the weight stream
+                        const MegaOp &nx = p.ops[oi + 1];
+                        if (nx.kind == MG_ATTN) {
+                            const int NC = p.attn_chunks;
+                            for (int unit = cta; unit < B * p.Hkv * NC; unit += nctas) {
+                                const int ch = unit % NC, bk = unit / NC;
+                                const int b = bk / p.Hkv, kvh = bk - b * p.Hkv;
+                                const int pos = p.d_pos[b];
+                                if (pos >= p.max_seq) continue;
+                                const int j_lo = pos - p.window > 0 ? pos - p.window : 0;
+                                const int per = (pos - j_lo + NC) / NC;
+                                const int j0 = j_lo + ch * per, j1 = min(pos, j0 + per);  // row `pos` is not written yet
+                                for (int pg = j0 / KV_PAGE; pg * KV_PAGE < j1; ++pg) {     // pages are the contiguous unit
+                                    const int ka = max(j0, pg * KV_PAGE), ke = min(j1, (pg + 1) * KV_PAGE);
+                                    const size_t off = (((size_t)p.page_table[(size_t)b * p.max_pages + pg] * p.Hkv + kvh) * KV_PAGE + (ka - pg * KV_PAGE)) * HD;
+                                    bulk_prefetch_l2(nx.kc + off, (uint32_t)(ke - ka) * HD * 4u);
+                                    bulk_prefetch_l2(nx.vc + off, (uint32_t)(ke - ka) * HD * 4u);
+                                }
+                            }
+                        }
+                    }
 #define yout ((track && p.logits_out) ? p.logits_out : vop->y)
 #define bias (vop->bias)
 #define resid (vop->res)
@@ -742,29 +768,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             prefetch_l1(reinterpret_cast<const unsigned char *>(&p.ops[oi + 1]) + 128);
         }
         if (kind == MG_MATVEC) {
-            if (tid == 0 && oi + 1 < p.n_ops && !(p.flags & 2)) {
-                // the next phase is this layer's attention: pull this CTA's chunk of the KV cache into L2 now, so the
-                // walk does not wait on DRAM behind the weight stream
-                const MegaOp &nx = p.ops[oi + 1];
-                if (nx.kind == MG_ATTN) {
-                    const int NC = p.attn_chunks;
-                    for (int unit = cta; unit < B * p.Hkv * NC; unit += nctas) {
-                        const int ch = unit % NC, bk = unit / NC;
-                        const int b = bk / p.Hkv, kvh = bk - b * p.Hkv;
-                        const int pos = p.d_pos[b];
-                        if (pos >= p.max_seq) continue;
-                        const int j_lo = pos - p.window > 0 ? pos - p.window : 0;
-                        const int per = (pos - j_lo + NC) / NC;
-                        const int j0 = j_lo + ch * per, j1 = min(pos, j0 + per);  // row `pos` is not written yet
-                        for (int pg = j0 / KV_PAGE; pg * KV_PAGE < j1; ++pg) {     // pages are the contiguous unit
-                            const int a = max(j0, pg * KV_PAGE), e = min(j1, (pg + 1) * KV_PAGE);
-                            const size_t off = (((size_t)p.page_table[(size_t)b * p.max_pages + pg] * p.Hkv + kvh) * KV_PAGE + (a - pg * KV_PAGE)) * HD;
-                            bulk_prefetch_l2(nx.kc + off, (uint32_t)(e - a) * HD * 4u);
-                            bulk_prefetch_l2(nx.vc + off, (uint32_t)(e - a) * HD * 4u);
-                        }
-                    }
-                }
-            }
             const int n_tiles = op.n_tiles, n_pairs = op.n_pairs, S = op.S, Ps = op.Ps, K = op.K;
             const int UT = op.unit_tiles;
             const bool has_norm = op.gamma != nullptr;
