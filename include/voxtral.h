@@ -108,7 +108,9 @@ int32_t vox_q4_tensor_create(const uint8_t *q4_bytes, size_t nbytes, int64_t n, 
                              int32_t device, vox_q4 **out);                      /* from_q4_bytes tensor.rs:35-71 */
 int32_t vox_q4_tensor_shape(const vox_q4 *w, int64_t *n, int64_t *k);
 int32_t vox_q4_tensor_dequantize(const vox_q4 *w, float *out /* [n*k] host */); /* dequantize tensor.rs:83-113 */
-/* y[b,m,:] = x[b,m,:] . W^T (+ bias); x [B,M,K] contiguous f32, y [B,M,N]; async on `stream` */
+/* y[b,m,:] = x[b,m,:] . W^T (+ bias); x [B,M,K] contiguous f32, y [B,M,N]; async on `stream`.
+ * A handle owns its split-K / operand-staging scratch: launches on ONE handle must be ordered (one stream, or
+ * event-ordered streams) -- the call is not reentrant per handle; distinct handles are independent. */
 int32_t vox_q4_matmul(const vox_q4 *w, const float *x_dev, float *y_dev, int32_t b, int32_t m,
                       const float *bias_dev /* nullable */, void *stream);
 /* host-buffer convenience (H2D, kernel, D2H, sync) -- what benches/q4_ops.rs:76-91 times */
